@@ -1,0 +1,137 @@
+// ctx.cuh — the lattice context behind the opaque `cet_ctx` of include/cetkmc.h, and the
+// error plumbing shared by all translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/cetkmc.h"
+#include "site_rates.cuh"
+
+namespace cet {
+
+void set_error(const char *fmt, ...);
+
+#define CET_CUDA(call)                                                                     \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            cet::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return 1000 + (int)e_;                                                         \
+        }                                                                                  \
+    } while (0)
+
+#define CET_REQUIRE(cond, ...)            \
+    do {                                  \
+        if (!(cond)) {                    \
+            cet::set_error(__VA_ARGS__);  \
+            return 1;                     \
+        }                                 \
+    } while (0)
+
+// Counters that live in device memory and are advanced by the single-CTA step kernel.
+struct KmcState {
+    int64_t steps_done, py_pos, np_pos, sp_pos, nucleation_count, fallback_last;
+    double total_time, last_total_rate;
+    int32_t terminated, starved;
+};
+
+struct SweepState {
+    unsigned long long n_fired, n_applied, n_nuc;   // running totals (device atomics)
+    unsigned int n_records, overflow;               // records appended by the current sweep
+    double sum_rate, max_rate;                      // totals of the rates seen by the last sweep
+    double tau, time;                               // interval of the next sweep; accumulated time
+    int32_t terminated, pad_;
+};
+
+}  // namespace cet
+
+// Device-memory layout (all arrays cover local planes [0, np) where np = ni + 2*halo and local
+// plane p holds global plane i_begin - halo + p; k is the fastest axis, then j, then plane):
+//   vox        u8   np*n1*n2   state | defects<<4
+//   vox_prev   u8   np*n1*n2   snapshot for the latent-heat term (allocated on first use)
+//   theta,phi  f64  np*n1*n2
+//   T, T2      f64  np*n1*n2   ping-pong buffers of the thermal stencil
+//   site_rate  f64  np*n1*n2   sum of the site's diff (occupied) or nuc+att (empty) rates
+//   dep_rate   f64  n1*n2      top plane only: deposition rate, NaN where no dep event exists
+//   row_occ / row_emp  f64  np*n1   per (plane, j) row sums split by occupancy class
+//   row_dep    f64  n1 ; row_depcnt i32 n1
+//   seg        f64  3*np       per-plane segment sums in list order: dep | occupied | empty
+//   total      f64  1 (+ n_dep i64)
+struct cet_ctx {
+    int device = 0;
+    int64_t n0 = 0, n1 = 0, n2 = 0;   // global extents (rates require n0 == n1 == n2 == L)
+    int64_t i_begin = 0, i_end = 0;   // owned global planes
+    int halo = 0;
+    int64_t np = 0;                   // local planes incl. ghosts
+    int64_t plane = 0;                // n1*n2
+    int64_t nloc = 0;                 // np*plane
+    bool cubic = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    uint8_t *vox = nullptr, *vox_prev = nullptr;
+    double *theta = nullptr, *phi = nullptr, *T = nullptr, *T2 = nullptr;
+    double *site_rate = nullptr, *dep_rate = nullptr;
+    double *row_occ = nullptr, *row_emp = nullptr, *row_dep = nullptr, *seg = nullptr;
+    int32_t *row_depcnt = nullptr;
+    double *total = nullptr;          // [0] total, [1] (as int64) n_dep
+    double *q_top = nullptr;
+    bool rates_valid = false;
+
+    // staging for host<->device conversion (grown on demand)
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
+
+    cet_rate_params rp;
+    bool have_rp = false;
+
+    // exact KMC
+    cet::KmcState *kmc = nullptr;
+    double *d_py = nullptr, *d_np = nullptr, *d_sp = nullptr;
+    size_t cap_py = 0, cap_np = 0, cap_sp = 0;
+    void *d_log = nullptr;
+    size_t cap_log = 0;
+
+    // sweep mode
+    cet::SweepState *sweep = nullptr;
+    unsigned long long *claim = nullptr;
+    void *records = nullptr;
+    size_t cap_records = 0;
+    int64_t sweep_index = 0;
+    double *blk_sum = nullptr, *blk_max = nullptr, *plane_sum = nullptr;
+    int64_t n_blk = 0;
+
+    // NCCL
+    void *nccl_comm = nullptr;
+    int rank = 0, world = 1;
+
+    cet::Lat lat() const
+    {
+        cet::Lat g;
+        g.vox = vox; g.theta = theta; g.phi = phi; g.T = T;
+        g.L = (int)n1;
+        g.i_off = (int)(i_begin - halo);
+        return g;
+    }
+    int64_t owned_offset() const { return (int64_t)halo * plane; }
+    int64_t owned_sites() const { return (i_end - i_begin) * plane; }
+};
+
+namespace cet {
+int ensure_stage(cet_ctx *c, size_t bytes);
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard()
+    {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+}  // namespace cet
