@@ -1,0 +1,41 @@
+// Test-only host build of csrc/site_rates.cuh: runs the product's per-site event enumeration
+// on the CPU so that its ordering and arithmetic can be checked against the oracle without a GPU.
+// Not part of the product (nothing in the package links or loads this).
+#include <stdint.h>
+#include <vector>
+#include "../../cet-driven-simulation-for-3d-printing-am-kmc-approach_b200/csrc/site_rates.cuh"
+
+using namespace cet;
+
+extern "C" long long hostsim_events(const uint8_t *vox, const double *theta, const double *phi, const double *T,
+                                    int L, const cet_rate_params *P, long long cap, uint8_t *type,
+                                    long long *pos, double *rate, long long *target, int32_t *atom)
+{
+    Lat g;
+    g.vox = vox; g.theta = theta; g.phi = phi; g.T = T; g.L = L; g.i_off = 0;
+    const long long LL = (long long)L * L;
+    long long n = 0;
+    auto put = [&](int ty, long long s, double r, long long t, int a) {
+        if (n < cap) { type[n] = (uint8_t)ty; pos[n] = s; rate[n] = r; target[n] = t; atom[n] = a; }
+        ++n;
+    };
+    for (int i = 0; i < L; ++i) {
+        if (i == L - 1)
+            for (int j = 0; j < L; ++j)
+                for (int k = 0; k < L; ++k) {
+                    const long long s = g.idx(i, j, k);
+                    double r;
+                    if (vox_state(vox[s]) == 0 && dep_rate(*P, T[s], &r)) put(CET_EV_DEP, s, r, -1, P->states_w);
+                }
+        for (int cls = 1; cls >= 0; --cls)     // occupied sites first, then empty ones
+            for (int j = 0; j < L; ++j)
+                for (int k = 0; k < L; ++k) {
+                    const long long s = g.idx(i, j, k);
+                    if ((vox_state(vox[s]) != 0) != (cls == 1)) continue;
+                    site_events(g, *P, i, j, k, [&](int ty, int slot, double r, int a) {
+                        put(ty, s, r, slot < 0 ? -1 : s + CET_NB_DI(slot) * LL + CET_NB_DJ(slot) * L + CET_NB_DK(slot), a);
+                    });
+                }
+    }
+    return n;
+}

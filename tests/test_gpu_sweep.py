@@ -1,0 +1,130 @@
+"""GPU: synchronous-sublattice sweeps (csrc/sweep.cu) — invariants, determinism and level-3
+parity (trajectory observables against the serial oracle within statistical bounds)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _sweep_params(cet, seed, L, eps=0.02, p_max=0.25, defect_fraction=0.0, thermal_every=0):
+    sp = cet._lib.SweepParams()
+    sp.seed, sp.events_per_sweep, sp.p_max = seed, eps * L ** 3, p_max
+    sp.defect_fraction, sp.thermal_every = defect_fraction, thermal_every
+    return sp
+
+
+def _setup(cet, L, seed=3, c=0.1):
+    from cetkmc import _synth
+    from cetkmc._config import rate_params
+    packed, th, ph, T = _synth.half_grown(L, seed=seed, grain=4)
+    ctx = cet.Context(L=L)
+    ctx.set_rate_params(rate_params(c))
+    st, df = _synth.unpack(packed)
+    ctx.upload(state=st, theta=th, phi=ph, T=T, defects=df)
+    return ctx, st, th, ph, T, df
+
+
+def test_sweep_is_deterministic_and_consistent(cet):
+    L = 40
+    outs = []
+    for _ in range(2):
+        ctx, st, th, ph, T, df = _setup(cet, L)
+        res = ctx.sweep_run(12, _sweep_params(cet, 11, L, defect_fraction=0.01), None)
+        outs.append((res, ctx.download(state=True, theta=True, phi=True), ctx.counts()))
+        ctx.close()
+    (r1, f1, c1), (r2, f2, c2) = outs
+    assert r1 == r2 and r1["events_applied"] > 0 and r1["events_applied"] <= r1["events_fired"]
+    assert not r1["overflow"] and not r1["terminated"]
+    for k in f1:
+        np.testing.assert_array_equal(f1[k], f2[k])
+    state, theta, phi = f1["state"], f1["theta"], f1["phi"]
+    assert state.min() >= 0 and state.max() <= 4
+    # empty and defect sites carry no orientation (kmc_simulation.py:289-301,323-327)
+    assert np.all(theta[state == 0] == 0.0) and np.all(phi[state == 0] == 0.0)
+    assert np.all(theta[state == 4] == 0.0)
+    assert np.all((theta >= 0) & (theta <= np.pi)) and np.all((phi >= 0) & (phi <= 2 * np.pi))
+    assert c1.sum() == L ** 3 and np.array_equal(c1, c2)
+
+
+def test_first_sweep_measures_only(cet, oracle):
+    """tau starts at 0: the first sweep evaluates every rate and fires nothing; its total equals
+    the oracle's total rate."""
+    L = 24
+    ctx, st, th, ph, T, df = _setup(cet, L)
+    res = ctx.sweep_run(1, _sweep_params(cet, 1, L), None)
+    assert res["events_fired"] == 0 and res["time"] == 0.0
+    ev = oracle.event_rates(st, th, ph, T, df, L, oracle.make_params(0.1))
+    assert abs(res["last_total_rate"] - oracle.pysum(ev["rate"])) <= 1e-11 * res["last_total_rate"]
+    o_sr, o_dep, _, _ = oracle.site_rates(st, th, ph, T, df, L, oracle.make_params(0.1))
+    o_sr[L - 1] += np.nan_to_num(o_dep)
+    assert abs(res["last_max_rate"] - o_sr.max()) <= 1e-12 * o_sr.max()
+    assert res["last_tau"] > 0
+    ctx.close()
+
+
+def test_diffusion_only_conserves_atoms(cet):
+    """Attachment, nucleation and deposition switched off (enormous bond energies make attachment
+    rates underflow, I0 = 0, a 1 K top plane): only diffusion of bond-free atoms can fire, which
+    must conserve the species counts and the multiset of orientations."""
+    from cetkmc import _synth
+    from cetkmc._config import rate_params
+    L = 32
+    packed, th, ph, T = _synth.half_grown(L, seed=8, grain=4, fill=0.08)
+    st, df = _synth.unpack(packed)
+    T = T.copy()
+    T[:] = 3000.0
+    T[L - 1] = 1.0                                   # deposition rate underflows to exactly 0
+    ctx = cet.Context(L=L)
+    rp = rate_params(0.0, overrides=dict(I0=0.0, E_B_W=1e6, E_B_RE=1e6, E_B_C=1e6))
+    ctx.set_rate_params(rp)
+    ctx.upload(state=st, theta=th, phi=ph, T=T, defects=df)
+    before = ctx.counts()
+    res = ctx.sweep_run(10, _sweep_params(cet, 5, L, eps=0.01), None)
+    after = ctx.counts()
+    f = ctx.download(state=True, theta=True)
+    ctx.close()
+    np.testing.assert_array_equal(before, after)
+    assert res["events_applied"] > 0
+    assert not np.array_equal(f["state"], st)
+    np.testing.assert_array_equal(np.sort(f["theta"][f["state"] > 0]), np.sort(th[st > 0]))
+
+
+def test_level3_observables_vs_serial_oracle(cet, oracle):
+    """Level-3 parity: over N seeds, the sublattice path and the serial oracle, run to the same
+    number of executed events from the same initial lattice, agree on occupied fraction, grain
+    count, Re fraction and equiaxed fraction within 4 standard errors + 3 % of the mean."""
+    from cetkmc import _host
+    from cetkmc._config import rate_params
+    L, n_events, n_seeds, c = 16, 1500, 6, 0.1
+    obs_o, obs_g = [], []
+    for seed in range(n_seeds):
+        st, th, ph, T, at = oracle.initialize_lattice(L, n_seeds=8, random_seed=seed, impurity_c=c)
+        df = np.zeros_like(st)
+        d = oracle.DrawStreams(seed=seed, n_py=2 * n_events, n_np=2 * n_events, n_sp=n_events * L * L)
+        o = [a.copy() for a in (st, at, th, ph, T)]
+        tp = oracle.make_thermal_params()
+        tp.every = 10 ** 9
+        r = oracle.kmc_run(o[0], o[1], o[2], o[3], o[4], df, L, oracle.make_params(c), 1, n_events, 0.0,
+                           d.py, d.np, d.sp, thermal=tp, log=False)
+        assert r["steps_done"] == n_events
+        m = _host.compute_metrics(o[0], o[2], o[3])
+        obs_o.append([(o[0] != 0).sum(), m["GrainCount"], (o[0] == 2).sum() / max((o[0] != 0).sum(), 1),
+                      m["EquiaxedFraction"]])
+        ctx = cet.Context(L=L)
+        ctx.set_rate_params(rate_params(c))
+        ctx.upload(state=st, theta=th, phi=ph, T=T, defects=df)
+        sp = _sweep_params(cet, 1000 + seed, L, eps=n_events / 60 / L ** 3, p_max=0.1)
+        applied = 0
+        while applied < n_events:
+            applied += ctx.sweep_run(1, sp, None)["events_applied"]
+        f = ctx.download(state=True, theta=True, phi=True)
+        ctx.close()
+        m = _host.compute_metrics(f["state"], f["theta"], f["phi"])
+        scale = n_events / applied                   # the last sweep overshoots by a few events
+        obs_g.append([(f["state"] != 0).sum() * scale, m["GrainCount"] * scale,
+                      (f["state"] == 2).sum() / max((f["state"] != 0).sum(), 1), m["EquiaxedFraction"]])
+    obs_o, obs_g = np.array(obs_o, dtype=float), np.array(obs_g, dtype=float)
+    mo, mg = obs_o.mean(0), obs_g.mean(0)
+    se = np.sqrt(obs_o.var(0, ddof=1) / n_seeds + obs_g.var(0, ddof=1) / n_seeds)
+    tol = 4 * se + 0.03 * np.abs(mo) + 1e-9
+    assert np.all(np.abs(mo - mg) <= tol), (mo, mg, tol)

@@ -1,0 +1,49 @@
+"""CPU: the product's per-site rate code (csrc/site_rates.cuh), compiled for the host by g++ as
+a test-only shim, against the oracle / reference fixtures.  Checks event set, order and rates of
+the device arithmetic before any GPU time is spent (the same header is what the kernels inline)."""
+import ctypes as C
+import glob
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, golden
+
+SRC = os.path.join(ROOT, "tests", "hostsim", "site_rates_host.cpp")
+OUT = os.path.join(ROOT, "tests", "hostsim", "_build")
+
+
+@pytest.fixture(scope="module")
+def hostsim():
+    os.makedirs(OUT, exist_ok=True)
+    so = os.path.join(OUT, "libhostsim.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, SRC],
+                   check=True)
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("name", sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "rates_*.npz"))))
+def test_site_events_match_reference(hostsim, name):
+    import cetkmc
+    from cetkmc._config import rate_params
+    g = golden(name)
+    L = g["state"].shape[0]
+    P = rate_params(float(g["impurity_c"]))
+    vox = (g["state"].astype(np.uint8) | (g["defects"].astype(np.uint8) << 4)).ravel()
+    cap = 16 * L ** 3
+    ty = np.zeros(cap, np.uint8); pos = np.zeros(cap, np.int64); rate = np.zeros(cap); tgt = np.zeros(cap, np.int64)
+    atom = np.zeros(cap, np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    hostsim.hostsim_events.restype = C.c_longlong
+    th, ph, T = (np.ascontiguousarray(g[k], dtype=np.float64) for k in ("theta", "phi", "T"))
+    n = hostsim.hostsim_events(vp(vox), vp(th), vp(ph), vp(T), L, C.byref(P), C.c_longlong(cap), vp(ty), vp(pos),
+                               vp(rate), vp(tgt), vp(atom))
+    assert n == g["ev_type"].size
+    np.testing.assert_array_equal(ty[:n], g["ev_type"])
+    np.testing.assert_array_equal(pos[:n], g["ev_pos"])
+    np.testing.assert_array_equal(tgt[:n], g["ev_target"])
+    nondep = g["ev_type"] != 0                      # species of dep events come from the draw stream
+    np.testing.assert_array_equal(atom[:n][nondep], g["ev_atom"][nondep])
+    np.testing.assert_allclose(rate[:n], g["ev_rate"], rtol=1e-13, atol=0.0)
