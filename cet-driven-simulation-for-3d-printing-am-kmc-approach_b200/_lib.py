@@ -73,6 +73,7 @@ SIGNATURES = {
     "cet_device_count": [C.POINTER(C.c_int)],
     "cet_device_name": [C.c_int, C.c_char_p, C.c_int],
     "cet_create": [C.POINTER(_VP), C.c_int, _I64, _I64, _I64, _I32],
+    "cet_create_slab": [C.POINTER(_VP), C.c_int, _I64, _I64, _I64, _I64, _I32],
     "cet_create_shape": [C.POINTER(_VP), C.c_int, _I64, _I64, _I64],
     "cet_destroy": [_VP],
     "cet_sync": [_VP],
@@ -103,6 +104,8 @@ SIGNATURES = {
     "cet_comm_destroy": [_VP],
     "cet_halo_exchange": [_VP, C.c_int],
     "cet_allreduce_f64": [_VP, _VP, C.c_int, C.c_int],
+    "cet_profile_enable": [_VP, C.c_int],
+    "cet_profile_read": [_VP, C.c_int, C.POINTER(_F64), C.POINTER(_I64), C.c_int],
     "cet_timer_begin": [_VP],
     "cet_timer_end_ms": [_VP, C.POINTER(C.c_float)],
 }
@@ -173,7 +176,10 @@ class Context:
     """One lattice (or one slab of planes [i_begin, i_end) with `halo` ghost planes per side)
     resident on one GPU."""
 
-    def __init__(self, L=None, shape=None, device=0, i_begin=0, i_end=None, halo=0):
+    def __init__(self, L=None, shape=None, device=0, i_begin=0, i_end=None, halo=0, n0=None):
+        """L: edge length (cubic lattice, the reference's case).  n0: number of planes along axis 0
+        when it differs from L (stacked slabs for multi-GPU weak scaling).  shape: thermal-only
+        context of arbitrary (n0, n1, n2)."""
         self._h = C.c_void_p(None)
         l = lib()
         if shape is not None and (L is None):
@@ -186,9 +192,11 @@ class Context:
             self.i_begin, self.i_end, self.halo = 0, n0, 0
         else:
             L = int(L)
-            i_end = L if i_end is None else int(i_end)
-            check(l.cet_create(C.byref(self._h), device, L, int(i_begin), i_end, int(halo)), "cet_create")
-            self.shape = (L, L, L)
+            n0 = L if n0 is None else int(n0)
+            i_end = n0 if i_end is None else int(i_end)
+            check(l.cet_create_slab(C.byref(self._h), device, n0, L, int(i_begin), i_end, int(halo)),
+                  "cet_create_slab")
+            self.shape = (n0, L, L)
             self.i_begin, self.i_end, self.halo = int(i_begin), i_end, int(halo)
         self.device = device
         self.owned_shape = (self.i_end - self.i_begin, self.shape[1], self.shape[2])
@@ -363,7 +371,22 @@ class Context:
         check(lib().cet_allreduce_f64(self._h, _ptr(v), v.size, op), "cet_allreduce_f64")
         return v
 
+    def sweep_reset(self):
+        check(lib().cet_sweep_reset(self._h), "cet_sweep_reset")
+
     # -- timing -----------------------------------------------------------------------------
+    PROF_KINDS = dict(decide=0, apply=1, thermal=2, rates=3, halo=4, step=5)
+
+    def profile_enable(self, on=True):
+        check(lib().cet_profile_enable(self._h, 1 if on else 0), "cet_profile_enable")
+
+    def profile_read(self, kind, reset=True):
+        """(total ms, launches) of a kernel kind since the last reset."""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        check(lib().cet_profile_read(self._h, self.PROF_KINDS[kind], C.byref(ms), C.byref(n), 1 if reset else 0),
+              "cet_profile_read")
+        return ms.value, n.value
+
     def timer_begin(self):
         check(lib().cet_timer_begin(self._h), "cet_timer_begin")
 

@@ -5,7 +5,7 @@ from __future__ import annotations
 import numpy as np
 
 
-def half_grown(L, seed=1234, grain=8, planes=None, fill=0.5):
+def half_grown(L, seed=1234, grain=8, planes=None, fill=0.5, n0=None):
     """'Half-grown' lattice: salt-and-pepper solid (W/Re/C/defect = .85/.10/.04/.01, `fill` of the
     sites) below a wavy front k < L/2 + 8 sin(2 pi i / L), empty above; orientations constant over
     grain^3 blocks; linear gradient T = 2800 + 895 k / L; defect flag on 5 % of the C sites.
@@ -13,7 +13,8 @@ def half_grown(L, seed=1234, grain=8, planes=None, fill=0.5):
     Returns (packed uint8 [state | defects << 4], theta, phi, T) for planes [p0, p1) of axis 0
     (default: all).  Every plane is generated from its own seeded stream, so a slab of a
     distributed lattice equals the same planes of the full one."""
-    p0, p1 = (0, L) if planes is None else planes
+    n0 = L if n0 is None else n0          # planes along axis 0 (stacked slabs when > L)
+    p0, p1 = (0, n0) if planes is None else planes
     n = p1 - p0
     packed = np.empty((n, L, L), dtype=np.uint8)
     theta = np.empty((n, L, L), dtype=np.float64)

@@ -66,11 +66,29 @@ __global__ void counts_kernel(const uint8_t *__restrict__ vox, int64_t n, unsign
     if (threadIdx.x < 16 && h[threadIdx.x]) atomicAdd(&out[threadIdx.x], (unsigned long long)h[threadIdx.x]);
 }
 
+__global__ void orient_kernel(const double *__restrict__ theta, const double *__restrict__ phi, double *vx,
+                              double *vy, double *vz, int64_t n)
+{
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n;
+         q += (int64_t)gridDim.x * blockDim.x)
+        unit_vector(theta[q], phi[q], &vx[q], &vy[q], &vz[q]);
+}
+
 static int grid_for(int64_t n, int block)
 {
     int64_t g = (n + block - 1) / block;
     const int64_t cap = 148 * 16;
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+int orient_update(cet_ctx *c, int64_t p_lo, int64_t p_hi)
+{
+    if (p_hi <= p_lo) return 0;
+    const int64_t off = p_lo * c->plane, n = (p_hi - p_lo) * c->plane;
+    orient_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->theta + off, c->phi + off, c->vx + off, c->vy + off,
+                                                            c->vz + off, n);
+    CET_CUDA(cudaGetLastError());
+    return 0;
 }
 
 static int create_common(cet_ctx **out, int device, int64_t n0, int64_t n1, int64_t n2,
@@ -115,6 +133,10 @@ static int create_common(cet_ctx **out, int device, int64_t n0, int64_t n1, int6
         CET_CUDA(cudaMalloc(&c->phi, c->nloc * sizeof(double)));
         CET_CUDA(cudaMemsetAsync(c->theta, 0, c->nloc * sizeof(double), c->stream));
         CET_CUDA(cudaMemsetAsync(c->phi, 0, c->nloc * sizeof(double), c->stream));
+        CET_CUDA(cudaMalloc(&c->vx, c->nloc * sizeof(double)));
+        CET_CUDA(cudaMalloc(&c->vy, c->nloc * sizeof(double)));
+        CET_CUDA(cudaMalloc(&c->vz, c->nloc * sizeof(double)));
+        if (int rc = orient_update(c, 0, c->np)) return rc;
         CET_CUDA(cudaMalloc(&c->site_rate, c->nloc * sizeof(double)));
         CET_CUDA(cudaMemsetAsync(c->site_rate, 0, c->nloc * sizeof(double), c->stream));
         CET_CUDA(cudaMalloc(&c->dep_rate, c->plane * sizeof(double)));
@@ -171,6 +193,11 @@ int cet_create(cet_ctx **ctx, int device, int64_t L, int64_t i_begin, int64_t i_
     return create_common(ctx, device, L, L, L, i_begin, i_end, halo, true);
 }
 
+int cet_create_slab(cet_ctx **ctx, int device, int64_t n0, int64_t L, int64_t i_begin, int64_t i_end, int32_t halo)
+{
+    return create_common(ctx, device, n0, L, L, i_begin, i_end, halo, true);
+}
+
 int cet_create_shape(cet_ctx **ctx, int device, int64_t n0, int64_t n1, int64_t n2)
 {
     return create_common(ctx, device, n0, n1, n2, 0, n0, 0, false);
@@ -184,12 +211,14 @@ int cet_destroy(cet_ctx *c)
     cet::DeviceGuard dg(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cet_comm_destroy(c);
-    void *ptrs[] = {c->vox, c->vox_prev, c->theta, c->phi, c->T, c->T2, c->site_rate, c->dep_rate,
+    void *ptrs[] = {c->vox, c->vox_prev, c->theta, c->phi, c->vx, c->vy, c->vz, c->T, c->T2, c->site_rate, c->dep_rate,
                     c->row_occ, c->row_emp, c->row_dep, c->row_depcnt, c->seg, c->total, c->q_top,
                     c->stage, c->kmc, c->d_py, c->d_np, c->d_sp, c->d_log, c->sweep, c->claim,
                     c->records, c->blk_sum, c->blk_max, c->plane_sum};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (auto &sp : c->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -246,6 +275,7 @@ int cet_upload(cet_ctx *c, const int64_t *state, const double *theta, const doub
         CET_REQUIRE(hbad == 0, "cet_upload: %s value outside 0..15 (one byte per voxel holds state | defects<<4)",
                     hbad == 1 ? "state" : "defects_mask");
     }
+    if (theta || phi) if (int rc = orient_update(c, c->halo, c->np - c->halo)) return rc;
     CET_CUDA(cudaStreamSynchronize(c->stream));
     c->rates_valid = false;
     return 0;
@@ -340,6 +370,9 @@ int cet_device_ptr(cet_ctx *c, int which, void **ptr, int64_t *nbytes)
         case 2: p = c->phi; nb = c->nloc * 8; break;
         case 3: p = c->T; nb = c->nloc * 8; break;
         case 4: p = c->site_rate; nb = c->nloc * 8; break;
+        case 5: p = c->vx; nb = c->nloc * 8; break;
+        case 6: p = c->vy; nb = c->nloc * 8; break;
+        case 7: p = c->vz; nb = c->nloc * 8; break;
         default: set_error("cet_device_ptr: unknown field %d", which); return 1;
     }
     CET_REQUIRE(p != nullptr, "cet_device_ptr: field %d not allocated for this context", which);
@@ -362,6 +395,36 @@ int cet_counts(cet_ctx *c, int64_t counts[16])
     CET_CUDA(cudaMemcpyAsync(h, c->stage, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CET_CUDA(cudaStreamSynchronize(c->stream));
     for (int q = 0; q < 16; ++q) counts[q] = (int64_t)h[q];
+    return 0;
+}
+
+int cet_profile_enable(cet_ctx *c, int on)
+{
+    CET_REQUIRE(c, "cet_profile_enable: NULL ctx");
+    c->profile = on != 0;
+    return 0;
+}
+
+int cet_profile_read(cet_ctx *c, int kind, double *ms_total, int64_t *launches, int reset)
+{
+    CET_REQUIRE(c && kind >= 0 && kind < cet::PROF_KINDS, "cet_profile_read: bad argument");
+    cet::DeviceGuard dg(c->device);
+    CET_CUDA(cudaStreamSynchronize(c->stream));
+    double tot = 0.0;
+    int64_t n = 0;
+    std::vector<cet_ctx::ProfSpan> keep;
+    for (auto &sp : c->prof_spans) {
+        if (sp.kind == kind) {
+            float ms = 0.f;
+            CET_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+            tot += ms; ++n;
+            if (reset) { c->prof_pool.push_back(sp.a); c->prof_pool.push_back(sp.b); continue; }
+        }
+        keep.push_back(sp);
+    }
+    c->prof_spans.swap(keep);
+    if (ms_total) *ms_total = tot;
+    if (launches) *launches = n;
     return 0;
 }
 

@@ -99,6 +99,10 @@ int comm_halo_exchange(cet_ctx *c, int fields)
         }
     }
     CET_NCCL(g_nccl.GroupEnd());
+    if (fields & 2) {          // orientation unit vectors of the refreshed ghost planes
+        if (lower >= 0) if (int rc = orient_update(c, 0, H)) return rc;
+        if (upper < c->world) if (int rc = orient_update(c, c->np - H, c->np)) return rc;
+    }
     return 0;
 }
 

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <vector>
 #include "../../include/cetkmc.h"
 #include "site_rates.cuh"
 
@@ -51,6 +52,8 @@ struct SweepState {
 //   vox        u8   np*n1*n2   state | defects<<4
 //   vox_prev   u8   np*n1*n2   snapshot for the latent-heat term (allocated on first use)
 //   theta,phi  f64  np*n1*n2
+//   vx,vy,vz   f64  np*n1*n2   orientation unit vectors (derived from theta/phi; kept in step by every
+//                              writer of theta/phi so the rate kernels never call sin/cos)
 //   T, T2      f64  np*n1*n2   ping-pong buffers of the thermal stencil
 //   site_rate  f64  np*n1*n2   sum of the site's diff (occupied) or nuc+att (empty) rates
 //   dep_rate   f64  n1*n2      top plane only: deposition rate, NaN where no dep event exists
@@ -72,6 +75,7 @@ struct cet_ctx {
 
     uint8_t *vox = nullptr, *vox_prev = nullptr;
     double *theta = nullptr, *phi = nullptr, *T = nullptr, *T2 = nullptr;
+    double *vx = nullptr, *vy = nullptr, *vz = nullptr;
     double *site_rate = nullptr, *dep_rate = nullptr;
     double *row_occ = nullptr, *row_emp = nullptr, *row_dep = nullptr, *seg = nullptr;
     int32_t *row_depcnt = nullptr;
@@ -102,6 +106,13 @@ struct cet_ctx {
     double *blk_sum = nullptr, *blk_max = nullptr, *plane_sum = nullptr;
     int64_t n_blk = 0;
 
+    // per-kernel-kind device timing (cet_profile_*): event pairs recorded around the dominant
+    // kernels on the context stream, resolved when the totals are read
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_pool;
+    struct ProfSpan { int kind; cudaEvent_t a, b; };
+    std::vector<ProfSpan> prof_spans;
+
     // NCCL
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
@@ -109,8 +120,8 @@ struct cet_ctx {
     cet::Lat lat() const
     {
         cet::Lat g;
-        g.vox = vox; g.theta = theta; g.phi = phi; g.T = T;
-        g.L = (int)n1;
+        g.vox = vox; g.vx = vx; g.vy = vy; g.vz = vz; g.T = T;
+        g.L = (int)n1; g.n0 = (int)n0;
         g.i_off = (int)(i_begin - halo);
         return g;
     }
@@ -120,6 +131,28 @@ struct cet_ctx {
 
 namespace cet {
 int ensure_stage(cet_ctx *c, size_t bytes);
+int orient_update(cet_ctx *c, int64_t p_lo, int64_t p_hi);   // v := unit_vector(theta, phi) on local planes
+enum { PROF_DECIDE = 0, PROF_APPLY = 1, PROF_THERMAL = 2, PROF_RATES = 3, PROF_HALO = 4, PROF_STEP = 5, PROF_KINDS = 6 };
+// RAII span: records an event pair around a launch when profiling is on.
+struct ProfScope {
+    cet_ctx *c; int kind; cudaEvent_t a = nullptr;
+    ProfScope(cet_ctx *ctx, int k) : c(ctx), kind(k)
+    {
+        if (!c->profile) return;
+        if (c->prof_pool.empty()) { if (cudaEventCreate(&a) != cudaSuccess) { a = nullptr; return; } }
+        else { a = c->prof_pool.back(); c->prof_pool.pop_back(); }
+        cudaEventRecord(a, c->stream);
+    }
+    ~ProfScope()
+    {
+        if (!a) return;
+        cudaEvent_t b = nullptr;
+        if (c->prof_pool.empty()) { if (cudaEventCreate(&b) != cudaSuccess) { c->prof_pool.push_back(a); return; } }
+        else { b = c->prof_pool.back(); c->prof_pool.pop_back(); }
+        cudaEventRecord(b, c->stream);
+        c->prof_spans.push_back({kind, a, b});
+    }
+};
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;

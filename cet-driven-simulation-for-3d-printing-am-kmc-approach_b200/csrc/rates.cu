@@ -13,10 +13,9 @@
 //   seg[3p+{0,1,2}]         : warp_strided_sum over j
 //   total                   : block_sum over seg
 //
-// Dense kernel shape: one warp per (plane, j) row, lanes stride k by 32 so every load of the
-// row and of its 14 neighbour rows is a coalesced 32-wide access; the 5 planes x 5 rows a warp
-// touches are shared with the other warps of the CTA (consecutive j) through L1.
+// Dense kernel shape: one warp per (plane, j) row — see dense_pass.cuh.
 #include "ctx.cuh"
+#include "dense_pass.cuh"
 #include "reduce.cuh"
 
 namespace cet {
@@ -31,51 +30,63 @@ struct RatesArgs {
     int p_lo, p_hi;   // local planes to evaluate
 };
 
+// dynamic shared memory per warp: rate_row[L] doubles, then the two uint16 index lists
+__host__ __device__ inline size_t dense_smem_per_warp(int L, bool with_rates)
+{
+    const size_t lists = (((size_t)2 * L * sizeof(uint16_t)) + 15) & ~(size_t)15;
+    return lists + (with_rates ? (size_t)L * sizeof(double) : 0);
+}
+
 __global__ void __launch_bounds__(RB_WARPS * 32) rates_rows_kernel(const RatesArgs a)
 {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int L = a.g.L;
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * RB_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int row = blockIdx.x * RB_WARPS + wid;
     const int nrows = (a.p_hi - a.p_lo) * L;
     if (row >= nrows) return;
     const int p = a.p_lo + row / L, j = row % L;
     const int i = a.g.i_off + p;
     const int64_t rbase = ((int64_t)p * L + j) * L;
-    double occ = 0.0, emp = 0.0;
-    for (int k = lane; k < L; k += 32) {
-        const double r = site_rate_sum(a.g, a.P, i, j, k, nullptr);
-        a.site_rate[rbase + k] = r;
-        if (vox_state(a.g.vox[rbase + k]) != 0) occ += r; else emp += r;
-    }
-    occ = warp_sum(occ);
-    emp = warp_sum(emp);
-    if (lane == 0) { a.row_occ[p * L + j] = occ; a.row_emp[p * L + j] = emp; }
-    if (i == L - 1) {                                        // deposition, top plane only
-        double ds = 0.0;
-        int dc = 0;
-        for (int k = lane; k < L; k += 32) {
-            double r = NAN;
-            if (vox_state(a.g.vox[rbase + k]) == 0) {
-                double v;
-                if (dep_rate(a.P, a.g.T[rbase + k], &v)) { r = v; ds += v; ++dc; }
-            }
-            a.dep_rate[j * L + k] = r;
+    unsigned char *mine = dyn_smem + wid * dense_smem_per_warp(L, true);
+    double *rate_row = (double *)mine;
+    RowLists w;
+    w.occ = (uint16_t *)(mine + (size_t)L * sizeof(double));
+    w.emp = w.occ + L;
+    const bool top = i == a.g.n0 - 1;
+    if (top)
+        for (int k = lane; k < L; k += 32) a.dep_rate[j * L + k] = NAN;    // empty sites overwrite below
+    row_classify(a.g, a.P, rbase, w, rate_row);
+    row_occupied(a.g, a.P, i, j, rbase, w, [&](int k, double sum, bool active) {
+        if (active) rate_row[k] = sum;
+    });
+    row_empty(a.g, a.P, i, j, rbase, w, [&](int k, double sum, bool has_dep, double dep, bool active) {
+        if (active) {
+            rate_row[k] = sum;
+            if (has_dep) a.dep_rate[j * L + k] = dep;
         }
-        ds = warp_sum(ds);
-        dc = warp_sum_i(dc);
+    });
+    __syncwarp();
+    for (int k = lane; k < L; k += 32) a.site_rate[rbase + k] = rate_row[k];
+    double occ, emp;
+    warp_row_sums(a.g.vox + rbase, rate_row, L, &occ, &emp);
+    if (lane == 0) { a.row_occ[p * L + j] = occ; a.row_emp[p * L + j] = emp; }
+    if (top) {
+        double ds; int dc;
+        warp_dep_row(a.dep_rate + j * L, L, &ds, &dc);
         if (lane == 0) { a.row_dep[j] = ds; a.row_depcnt[j] = dc; }
     }
 }
 
 // One warp per local plane: plane-segment sums in list order.
 __global__ void seg_kernel(const double *row_occ, const double *row_emp, const double *row_dep,
-                           double *seg, int n1, int p_lo, int p_hi, int i_off, int L)
+                           double *seg, int n1, int p_lo, int p_hi, int i_off, int n0)
 {
     const int p = p_lo + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (p >= p_hi) return;
     const double so = warp_strided_sum(row_occ + (int64_t)p * n1, n1);
     const double se = warp_strided_sum(row_emp + (int64_t)p * n1, n1);
-    const double sd = (i_off + p == L - 1) ? warp_strided_sum(row_dep, n1) : 0.0;
+    const double sd = (i_off + p == n0 - 1) ? warp_strided_sum(row_dep, n1) : 0.0;
     if ((threadIdx.x & 31) == 0) { seg[3 * p + 0] = sd; seg[3 * p + 1] = so; seg[3 * p + 2] = se; }
 }
 
@@ -100,11 +111,19 @@ int rates_build(cet_ctx *c)
     a.row_occ = c->row_occ; a.row_emp = c->row_emp; a.row_dep = c->row_dep; a.row_depcnt = c->row_depcnt;
     a.p_lo = c->halo; a.p_hi = (int)(c->np - c->halo);
     const int nrows = (a.p_hi - a.p_lo) * (int)c->n1;
-    rates_rows_kernel<<<(nrows + RB_WARPS - 1) / RB_WARPS, RB_WARPS * 32, 0, c->stream>>>(a);
+    CET_REQUIRE(c->n1 <= 65535, "rates: L must fit 16-bit row indices");
+    const size_t smem = RB_WARPS * dense_smem_per_warp((int)c->n1, true);
+    CET_REQUIRE(smem <= 220 * 1024, "rates: L=%lld needs %zu B of shared memory per CTA", (long long)c->n1, smem);
+    if (smem > 48 * 1024)
+        CET_CUDA(cudaFuncSetAttribute(rates_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        ProfScope ps(c, PROF_RATES);
+        rates_rows_kernel<<<(nrows + RB_WARPS - 1) / RB_WARPS, RB_WARPS * 32, smem, c->stream>>>(a);
+    }
     CET_CUDA(cudaGetLastError());
     const int npl = a.p_hi - a.p_lo;
     seg_kernel<<<(npl + 3) / 4, 128, 0, c->stream>>>(c->row_occ, c->row_emp, c->row_dep, c->seg, (int)c->n1,
-                                                     a.p_lo, a.p_hi, a.g.i_off, a.g.L);
+                                                     a.p_lo, a.p_hi, a.g.i_off, a.g.n0);
     CET_CUDA(cudaGetLastError());
     total_kernel<<<1, 256, 0, c->stream>>>(c->seg, c->row_depcnt, c->total, a.p_lo, a.p_hi, (int)c->n1,
                                            c->i_end == c->n0 ? 1 : 0);
@@ -166,7 +185,7 @@ __global__ void __launch_bounds__(256) export_kernel(const ExportArgs a)
     const int64_t LL = (int64_t)L * L;
     const int nsite = L * L;
     for (int segm = 0; segm < 3; ++segm) {
-        if (segm == 0 && i != L - 1) {
+        if (segm == 0 && i != a.g.n0 - 1) {
             if (!WRITE && threadIdx.x == 0) a.plane_counts[3 * pl] = 0;
             continue;
         }

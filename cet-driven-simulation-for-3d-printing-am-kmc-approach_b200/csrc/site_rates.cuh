@@ -1,15 +1,21 @@
-// site_rates.cuh — per-site event enumeration and Arrhenius rates.
+// site_rates.cuh — per-site event enumeration and Arrhenius rates (kmc_event_rates.py:43-160).
 //
-// One function, `site_events`, produces the events of ONE lattice site in exactly the
-// order the reference appends them (kmc_event_rates.py:75-109 for an occupied site,
-// :112-158 for an empty one) and with the reference's floating-point evaluation order.
-// Every consumer — the dense rate kernel, the neighbour-rate update after an event, the
-// event-list export and the BKL search inside a site — goes through it, so a rate computed
-// incrementally is bit-identical to the one a full rebuild produces.
+// Building blocks, shared by EVERY consumer (dense rate kernel, sweep kernel, incremental
+// refresh after an event, event-list export, event pick inside a site) so that a rate computed
+// by any of them has the same bits:
+//     occ_prep / diff_pair_rate    occupied site  -> diffusion events    (:79-109)
+//     emp_prep / att_pair_rate     empty site     -> nucleation + attachment events (:116-158)
+//     dep_rate                     empty top-plane site -> deposition event (:55-72)
+//     site_events                  the events of one site in the reference's list order
 //
-// The file compiles for the device (nvcc) and for the host (g++, tests/hostsim only: the
-// host build exists to check this arithmetic against the oracle without a GPU; it is not a
-// product code path).
+// Differences from a literal transcription, all within the stated 1e-12 relative tolerance:
+//   * orientations enter through resident unit vectors v = (sin t cos p, sin t sin p, cos t)
+//     kept in HBM beside theta/phi (kmc_event_rates.py:11-20 recomputes them per pair: 8
+//     trigonometric calls per attachment event); cos(arccos(dot)) (:23,:155) is taken as dot;
+//   * x / y inside a rate is x * rcp(y) with a Newton-refined reciprocal (<= 1 ulp).
+//
+// The file also compiles for the host (g++, tests/hostsim only — a checker for this arithmetic
+// that needs no GPU; not a product code path).
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -29,10 +35,39 @@ CET_HD double pymax(double a, double b) { return (b > a) ? b : a; }
 CET_HD double pymin(double a, double b) { return (b < a) ? b : a; }
 CET_HD bool finite_f64(double x) { return (x - x) == 0.0; }
 
+// 1/x for normal positive x: hardware seed + two Newton steps on the device.
+CET_HD double rcp(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = __fma_rn(r, __fma_rn(-x, r, 1.0), r);
+    r = __fma_rn(r, __fma_rn(-x, r, 1.0), r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+
 // kmc_event_rates.py:29-36 — offset order of get_bcc_neighbors
 #define CET_NB_DI(o) ((o) < 2 ? 1 : (o) < 4 ? -1 : (o) == 8 ? 2 : (o) == 9 ? -2 : 0)
 #define CET_NB_DJ(o) ((o) == 0 || (o) == 2 || (o) == 4 || (o) == 5 ? 1 : ((o) == 1 || (o) == 3 || (o) == 6 || (o) == 7) ? -1 : (o) == 10 ? 2 : (o) == 11 ? -2 : 0)
 #define CET_NB_DK(o) ((o) == 4 || (o) == 6 ? 1 : ((o) == 5 || (o) == 7) ? -1 : (o) == 12 ? 2 : (o) == 13 ? -2 : 0)
+
+// The same table as data, for loops that are deliberately NOT unrolled (the fully unrolled form
+// of the 14-slot loops with an inlined fp64 exp per slot is ~140 KB of SASS and stalls on
+// instruction fetch; see profiles/).
+#define CET_NB_TABLE_INIT {{1, 1, 0}, {1, -1, 0}, {-1, 1, 0}, {-1, -1, 0}, {0, 1, 1}, {0, 1, -1}, {0, -1, 1}, \
+                           {0, -1, -1}, {2, 0, 0}, {-2, 0, 0}, {0, 2, 0}, {0, -2, 0}, {0, 0, 2}, {0, 0, -2}}
+static const int8_t h_nb_off[14][3] = CET_NB_TABLE_INIT;
+#if defined(__CUDACC__)
+static __constant__ int8_t c_nb_off[14][3] = CET_NB_TABLE_INIT;
+#endif
+#if defined(__CUDA_ARCH__)
+#define CET_NB_TAB c_nb_off
+#else
+#define CET_NB_TAB h_nb_off
+#endif
 
 // Packed voxel byte: low nibble = state (0 empty, 1 W, 2 Re, 3 C, 4 defect), high nibble =
 // defects_mask value.
@@ -42,22 +77,49 @@ CET_HD int vox_defects(uint8_t v) { return v >> 4; }
 // View of the lattice (or of one slab of it with ghost planes) in device memory.
 struct Lat {
     const uint8_t *vox;
-    const double *theta, *phi, *T;
-    int L;       // global edge length (i, j and k all run over [0, L))
+    const double *vx, *vy, *vz, *T;
+    int L;       // edge length of axes 1 and 2
+    int n0;      // global number of planes along axis 0 (== L for the reference's cubic lattices)
     int i_off;   // global i of local plane 0
     CET_HD int64_t idx(int i, int j, int k) const { return ((int64_t)(i - i_off) * L + j) * L + k; }
+    CET_HD int64_t nb(int64_t s, int o) const
+    {
+        return s + ((int64_t)CET_NB_TAB[o][0] * L + CET_NB_TAB[o][1]) * L + CET_NB_TAB[o][2];
+    }
 };
 
-// kmc_event_rates.py:10-23 compute_misorientation, followed by cos() as used at :155.
-// Returns cos(arccos(clamp(v1.v2))).
-CET_HD double cos_misorientation(double t1, double p1, double t2, double p2)
+// In-bounds mask of the 14 neighbours (bit o set <=> get_bcc_neighbors keeps offset o).
+CET_HD unsigned inbounds_mask_ij(int i, int j, int n0, int L)      // the part that depends on the row only
 {
-    double s1 = sin(t1), c1 = cos(t1), s2 = sin(t2), c2 = cos(t2);
-    double v1x = s1 * cos(p1), v1y = s1 * sin(p1);
-    double v2x = s2 * cos(p2), v2y = s2 * sin(p2);
-    double dot = v1x * v2x + v1y * v2y + c1 * c2;
-    dot = pymax(pymin(dot, 1.0), -1.0);
-    return cos(acos(dot));
+    unsigned m = 0x3FFFu;
+    if (i + 1 >= n0) m &= ~0x0003u;      // slots 0,1: di = +1
+    if (i - 1 < 0) m &= ~0x000Cu;        // slots 2,3: di = -1
+    if (i + 2 >= n0) m &= ~0x0100u;      // slot 8
+    if (i - 2 < 0) m &= ~0x0200u;        // slot 9
+    if (j + 1 >= L) m &= ~0x0035u;       // slots 0,2,4,5: dj = +1
+    if (j - 1 < 0) m &= ~0x00CAu;        // slots 1,3,6,7: dj = -1
+    if (j + 2 >= L) m &= ~0x0400u;       // slot 10
+    if (j - 2 < 0) m &= ~0x0800u;        // slot 11
+    return m;
+}
+CET_HD unsigned inbounds_mask_k(unsigned m, int k, int L)          // ... and the per-site part
+{
+    if (k + 1 >= L) m &= ~0x0050u;       // slots 4,6: dk = +1
+    if (k - 1 < 0) m &= ~0x00A0u;        // slots 5,7: dk = -1
+    if (k + 2 >= L) m &= ~0x1000u;       // slot 12
+    if (k - 2 < 0) m &= ~0x2000u;        // slot 13
+    return m;
+}
+CET_HD unsigned inbounds_mask(int i, int j, int k, int n0, int L)
+{
+    return inbounds_mask_k(inbounds_mask_ij(i, j, n0, L), k, L);
+}
+
+// Orientation unit vector (kmc_event_rates.py:11-15).
+CET_HD void unit_vector(double theta, double phi, double *x, double *y, double *z)
+{
+    const double st = sin(theta);
+    *x = st * cos(phi); *y = st * sin(phi); *z = cos(theta);
 }
 
 // Deposition rate of an empty top-plane site (kmc_event_rates.py:60-64).  Returns false when
@@ -79,6 +141,111 @@ CET_HD int dep_species(const cet_rate_params &P, double r)
     return P.states_w;
 }
 
+// ---- occupied site: diffusion (kmc_event_rates.py:79-109) ------------------------------------
+struct OccPrep { double local_T, boltz; };
+
+CET_HD OccPrep occ_prep(const cet_rate_params &P, int self_state, int defects, double T_self, int n_bonds)
+{
+    double E_b_atom, E_diff_atom;
+    if (self_state == P.states_w) { E_b_atom = P.E_b[0]; E_diff_atom = P.E_diff[0]; }
+    else if (self_state == P.states_re) { E_b_atom = P.E_b[1]; E_diff_atom = P.E_diff[1]; }
+    else { E_b_atom = P.E_b[2]; E_diff_atom = P.E_diff[2]; }
+    OccPrep q;
+    q.local_T = pymax(T_self, 1.0);
+    const double defect_factor = 1.0 + (double)defects;
+    const double E_tot = pymax(E_diff_atom + 0.1 * (double)n_bonds * E_b_atom, 0.0);
+    q.boltz = exp(-defect_factor * E_tot * rcp(P.kT * q.local_T));
+    return q;
+}
+
+// rate of the diffusion event into an empty neighbour whose raw temperature is Tn_raw;
+// returns 0 when the event is filtered (:108)
+CET_HD double diff_pair_rate(const cet_rate_params &P, const OccPrep &q, double Tn_raw)
+{
+    const double neighbor_T = pymax(Tn_raw, 1.0);
+    const double dT = fabs(q.local_T - neighbor_T);
+    const double denom = pymax(P.T_melt - neighbor_T, 1.0);
+    const double grad_factor = 1.0 + 0.1 * dT * rcp(denom);
+    const double rate = P.nu * grad_factor * q.boltz;
+    return (rate > P.rate_threshold && finite_f64(rate)) ? rate : 0.0;
+}
+
+// ---- empty site: nucleation + attachment (kmc_event_rates.py:116-158) --------------------------
+struct EmpPrep {
+    double nuc_rate;     // 0 when there is no nucleation event
+    double inv_kTT;      // 1 / (kT * local_T)
+    double gfac;         // 1 + ANISOTROPY * max(0, grad_z) / max(T_melt - local_T, 1)
+};
+
+CET_HD EmpPrep emp_prep(const cet_rate_params &P, double T_self, double T_km, double T_kp, int n_imp, int n_in)
+{
+    EmpPrep q;
+    const double local_T = pymax(T_self, 1.0);
+    const double dT = P.T_melt - local_T;
+    q.inv_kTT = rcp(P.kT * local_T);
+    q.nuc_rate = 0.0;
+    if (dT > P.delta_T_c) {                                      // :120-132
+        const double f_imp = pymin(P.max_imp_fraction, (double)n_imp / (double)(n_in > 1 ? n_in : 1));
+        double K_eff = P.k_nuc * (1.0 - P.beta_imp_nuc * f_imp);
+        K_eff = pymax(0.1 * P.k_nuc, pymin(P.k_nuc, K_eff));
+        const double barrier = K_eff * rcp(pymax((dT + 1e-6) * (dT + 1e-6), 1e-6));
+        const double rate = P.i0 * exp(-barrier * q.inv_kTT);
+        if (rate > P.rate_threshold && finite_f64(rate)) q.nuc_rate = rate;
+    }
+    const double grad_z = (T_kp - T_km) * 0.5;                   // :151-154
+    q.gfac = 1.0 + P.anisotropy * (pymax(0.0, grad_z) * rcp(pymax(P.T_melt - local_T, 1.0)));
+    return q;
+}
+
+// rate of the attachment event copying occupied neighbour n (species index ia = 0 W, 1 Re, 2 C);
+// returns 0 when filtered (:157)
+CET_HD double att_pair_rate(const cet_rate_params &P, const EmpPrep &q, int ia, double sx, double sy, double sz,
+                            double nx, double ny, double nz)
+{
+    double dot = sx * nx + sy * ny + sz * nz;
+    dot = pymax(pymin(dot, 1.0), -1.0);
+    const double E_att = 0.5 * P.E_b[ia] * (1.0 - dot);
+    const double rate = P.nu * exp(-E_att * q.inv_kTT) * q.gfac;
+    return (rate > P.rate_threshold && finite_f64(rate)) ? rate : 0.0;
+}
+
+CET_HD int species_index(const cet_rate_params &P, int st)
+{
+    return st == P.states_w ? 0 : st == P.states_re ? 1 : st == P.states_c ? 2 : -1;
+}
+
+// Neighbour states of site s packed 4 bits per offset (0 for out-of-bounds offsets).
+CET_HD uint64_t neighbour_states(const Lat &g, int64_t s, unsigned inb)
+{
+    uint64_t nst = 0;
+#pragma unroll 1
+    for (int o = 0; o < 14; ++o)
+        if (inb >> o & 1u) nst |= (uint64_t)vox_state(g.vox[g.nb(s, o)]) << (4 * o);
+    return nst;
+}
+
+// SWAR helpers on the packed neighbour states: a mask with bit 4*o set for every slot whose
+// nibble is non-zero / equals `value` (1..15).
+#define CET_NIB_LSB 0x0011111111111111ull
+CET_HD uint64_t nib_nonzero(uint64_t x) { return (x | (x >> 1) | (x >> 2) | (x >> 3)) & CET_NIB_LSB; }
+CET_HD uint64_t nib_equals(uint64_t x, int value) { return ~nib_nonzero(x ^ (CET_NIB_LSB * (uint64_t)value)) & CET_NIB_LSB; }
+CET_HD int popc64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+CET_HD int popc32(unsigned x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+
 // Enumerate the diff events (occupied site) or nuc+att events (empty site) of site (i,j,k)
 // in reference order.  emit(type, slot, rate, atom): slot = index 0..13 into the offset table
 // of the target / source neighbour, or -1 for nuc.
@@ -87,95 +254,39 @@ CET_HD void site_events(const Lat &g, const cet_rate_params &P, int i, int j, in
 {
     const int L = g.L;
     const int64_t s = g.idx(i, j, k);
-    const int64_t LL = (int64_t)L * L;
-    const int self = vox_state(g.vox[s]);
-
-    // in-bounds mask + neighbour states (both loops of the reference walk the same list)
-    unsigned inb = 0;
-    int nstate[14];
-    int n_in = 0;
-#pragma unroll
-    for (int o = 0; o < 14; ++o) {
-        const int ni = i + CET_NB_DI(o), nj = j + CET_NB_DJ(o), nk = k + CET_NB_DK(o);
-        const bool ok = ni >= 0 && ni < L && nj >= 0 && nj < L && nk >= 0 && nk < L;
-        nstate[o] = 0;
-        if (ok) {
-            inb |= 1u << o;
-            ++n_in;
-            nstate[o] = vox_state(g.vox[s + CET_NB_DI(o) * LL + CET_NB_DJ(o) * L + CET_NB_DK(o)]);
-        }
-    }
+    const uint8_t v = g.vox[s];
+    const int self = vox_state(v);
+    const unsigned inb = inbounds_mask(i, j, k, g.n0, L);
+    const uint64_t nst = neighbour_states(g, s, inb);
+    const int n_in = popc32(inb), n_bonds = popc64(nib_nonzero(nst));
 
     if (self != 0) {
-        // ---- occupied: diffusion, kmc_event_rates.py:79-109
         if (self == P.defect_id) return;                         // :80-81
-        double E_b_atom, E_diff_atom;
-        if (self == P.states_w) { E_b_atom = P.E_b[0]; E_diff_atom = P.E_diff[0]; }
-        else if (self == P.states_re) { E_b_atom = P.E_b[1]; E_diff_atom = P.E_diff[1]; }
-        else { E_b_atom = P.E_b[2]; E_diff_atom = P.E_diff[2]; }
-        const double local_T = pymax(g.T[s], 1.0);
-        const double defect_factor = 1.0 + (double)vox_defects(g.vox[s]);
-        int n_bonds = 0;
-#pragma unroll
-        for (int o = 0; o < 14; ++o)
-            if ((inb >> o & 1u) && nstate[o] != 0) ++n_bonds;
         if (n_bonds == n_in) return;                             // no empty neighbour: no event
-        const double E_tot = pymax(E_diff_atom + 0.1 * (double)n_bonds * E_b_atom, 0.0);
-        const double boltz = exp(-defect_factor * E_tot / (P.kT * local_T));
-#pragma unroll
+        const OccPrep q = occ_prep(P, self, vox_defects(v), g.T[s], n_bonds);
+#pragma unroll 1
         for (int o = 0; o < 14; ++o) {
-            if (!(inb >> o & 1u) || nstate[o] != 0) continue;
-            const double neighbor_T =
-                pymax(g.T[s + CET_NB_DI(o) * LL + CET_NB_DJ(o) * L + CET_NB_DK(o)], 1.0);
-            const double dT = fabs(local_T - neighbor_T);
-            const double denom = pymax(P.T_melt - neighbor_T, 1.0);
-            const double grad_factor = 1.0 + 0.1 * dT / denom;
-            const double rate = P.nu * grad_factor * boltz;
-            if (rate > P.rate_threshold && finite_f64(rate)) emit((int)CET_EV_DIFF, o, rate, self);
+            if (!(inb >> o & 1u) || ((nst >> (4 * o)) & 15) != 0) continue;
+            const double rate = diff_pair_rate(P, q, g.T[g.nb(s, o)]);
+            if (rate != 0.0) emit((int)CET_EV_DIFF, o, rate, self);
         }
         return;
     }
 
-    // ---- empty: nucleation + attachment, kmc_event_rates.py:116-158
-    const double local_T = pymax(g.T[s], 1.0);
-    const double dT = P.T_melt - local_T;
-    if (dT > P.delta_T_c) {                                      // :120-132
-        int n_imp = 0;
-#pragma unroll
-        for (int o = 0; o < 14; ++o)
-            if ((inb >> o & 1u) && (nstate[o] == P.states_re || nstate[o] == P.states_c)) ++n_imp;
-        const double f_imp = pymin(P.max_imp_fraction, (double)n_imp / (double)(n_in > 1 ? n_in : 1));
-        double K_eff = P.k_nuc * (1.0 - P.beta_imp_nuc * f_imp);
-        K_eff = pymax(0.1 * P.k_nuc, pymin(P.k_nuc, K_eff));
-        const double barrier = K_eff / pymax((dT + 1e-6) * (dT + 1e-6), 1e-6);
-        const double rate = P.i0 * exp(-barrier / (P.kT * local_T));
-        if (rate > P.rate_threshold && finite_f64(rate)) emit((int)CET_EV_NUC, -1, rate, P.states_w);
-    }
-    bool have_self = false;
-    double th_s = 0.0, ph_s = 0.0, gfac = 0.0, kTT = 0.0;
-#pragma unroll
+    const int n_imp = popc64(nib_equals(nst, P.states_re)) + popc64(nib_equals(nst, P.states_c));
+    const int km = k - 1 > 0 ? k - 1 : 0, kp = k + 1 < L - 1 ? k + 1 : L - 1;
+    const EmpPrep q = emp_prep(P, g.T[s], g.T[s + (km - k)], g.T[s + (kp - k)], n_imp, n_in);
+    if (q.nuc_rate != 0.0) emit((int)CET_EV_NUC, -1, q.nuc_rate, P.states_w);
+    if (n_bonds == 0) return;
+    const double sx = g.vx[s], sy = g.vy[s], sz = g.vz[s];
+#pragma unroll 1
     for (int o = 0; o < 14; ++o) {                               // :135-158
-        if (!(inb >> o & 1u)) continue;
-        const int na = nstate[o];
-        if (na == 0) continue;
-        int ia;
-        if (na == P.states_w) ia = 0;
-        else if (na == P.states_re) ia = 1;
-        else if (na == P.states_c) ia = 2;
-        else continue;
-        if (!have_self) {
-            have_self = true;
-            th_s = g.theta[s]; ph_s = g.phi[s];
-            const int km = k - 1 > 0 ? k - 1 : 0, kp = k + 1 < L - 1 ? k + 1 : L - 1;
-            const double grad_z = (g.T[s + (kp - k)] - g.T[s + (km - k)]) * 0.5;
-            gfac = 1.0 + P.anisotropy * (pymax(0.0, grad_z) / pymax(P.T_melt - local_T, 1.0));
-            kTT = P.kT * local_T;
-        }
-        const int64_t t = s + CET_NB_DI(o) * LL + CET_NB_DJ(o) * L + CET_NB_DK(o);
-        const double cm = cos_misorientation(th_s, ph_s, g.theta[t], g.phi[t]);
-        const double E_att = 0.5 * P.E_b[ia] * (1.0 - cm);
-        const double rate = P.nu * exp(-E_att / kTT) * gfac;
-        if (rate > P.rate_threshold && finite_f64(rate)) emit((int)CET_EV_ATT, o, rate, na);
+        const int na = (int)(nst >> (4 * o)) & 15;
+        const int ia = species_index(P, na);
+        if (na == 0 || ia < 0) continue;
+        const int64_t t = g.nb(s, o);
+        const double rate = att_pair_rate(P, q, ia, sx, sy, sz, g.vx[t], g.vy[t], g.vz[t]);
+        if (rate != 0.0) emit((int)CET_EV_ATT, o, rate, na);
     }
 }
 

@@ -21,6 +21,7 @@
 // exchange per sweep (comm.cu) is the only data-path communication.  Plane sums are combined
 // in a fixed order so the trajectory is independent of the number of slabs.
 #include "ctx.cuh"
+#include "dense_pass.cuh"
 #include "reduce.cuh"
 
 namespace cet {
@@ -62,6 +63,7 @@ struct Record {          // one fired event
 
 struct SweepArgs {
     Lat g;
+    const double *theta, *phi;
     cet_rate_params P;
     SweepState *ss;
     Record *records;
@@ -87,8 +89,64 @@ __device__ __forceinline__ unsigned long long claim_key(int rank, long long gsit
     return ((unsigned long long)(125 - rank) << 48) | (unsigned long long)(gsite + 1);
 }
 
-__global__ void __launch_bounds__(SW_WARPS * 32) sweep_decide_kernel(const SweepArgs a)
+// A site fired: pick one of its events with probability rate / R (list order: dep first, then the
+// site's own events), record it and claim the sites it writes.
+__device__ __noinline__ void fire_event(const SweepArgs &a, int i, int j, int k, int64_t s, long long gsite,
+                                        double R, double dep, bool has_dep, double u_pick)
 {
+    const cet_rate_params &P = a.P;
+    const int L = a.g.L;
+    const int64_t LL = (int64_t)L * L;
+    const double x = u_pick * R;
+    double cum = 0.0;
+    int ety = -1, eslot = -1, eatom = 0;
+    bool found = false;
+    if (has_dep) {
+        cum = dep; ety = CET_EV_DEP; eatom = P.states_w;
+        if (cum >= x) found = true;
+    }
+    if (!found)
+        site_events(a.g, P, i, j, k, [&](int ty, int slot, double rate, int atom) {
+            if (found) return;
+            cum += rate; ety = ty; eslot = slot; eatom = atom;
+            if (cum >= x) found = true;
+        });
+    if (ety < 0) return;
+    Record rec;
+    rec.src = s;
+    rec.theta = 0.0; rec.phi = 0.0;
+    int64_t tgt = -1;
+    if (ety == CET_EV_DEP || ety == CET_EV_NUC) {
+        double ut, up;
+        philox_u2(a.seed, (uint64_t)gsite, a.sweep, 1u, &ut, &up);
+        rec.theta = __dmul_rn(3.141592653589793, ut);          // np.random.uniform(0, pi)
+        rec.phi = __dmul_rn(2 * 3.141592653589793, up);        // np.random.uniform(0, 2pi)
+        if (ety == CET_EV_DEP) {                               // kmc_event_rates.py:65-71
+            double us, unused;
+            philox_u2(a.seed, (uint64_t)gsite, a.sweep, 2u, &us, &unused);
+            eatom = dep_species(P, us);
+        }
+    } else {
+        tgt = s + CET_NB_DI(eslot) * LL + CET_NB_DJ(eslot) * L + CET_NB_DK(eslot);
+        if (ety == CET_EV_ATT) { rec.theta = a.theta[tgt]; rec.phi = a.phi[tgt]; }
+        else { rec.theta = a.theta[s]; rec.phi = a.phi[s]; }
+    }
+    const int rank = colour_rank(i, j, k, a.sweep);
+    rec.info = ety | ((eslot + 1) << 4) | (eatom << 12);
+    rec.colour_rank = rank;
+    const unsigned int slot = atomicAdd(&a.ss->n_records, 1u);
+    if (slot >= a.cap_records) { a.ss->overflow = 1; return; }
+    const unsigned long long key = claim_key(rank, gsite);
+    atomicMax(&a.claim[s], key);
+    if (ety == CET_EV_DIFF) atomicMax(&a.claim[tgt], key);
+    a.records[slot] = rec;
+}
+
+// __grid_constant__: the argument block stays in constant memory even though fire_event takes
+// its address (no per-thread stack copy).
+__global__ void __launch_bounds__(SW_WARPS * 32) sweep_decide_kernel(const __grid_constant__ SweepArgs a)
+{
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ double s_sum[SW_WARPS], s_max[SW_WARPS];
     const int L = a.g.L;
     const int64_t LL = (int64_t)L * L;
@@ -101,68 +159,33 @@ __global__ void __launch_bounds__(SW_WARPS * 32) sweep_decide_kernel(const Sweep
     double rsum = 0.0, rmax = 0.0;
     if (j < L && !stop) {
         const int64_t rbase = ((int64_t)p * L + j) * L;
-        for (int k = lane; k < L; k += 32) {
-            const int64_t s = rbase + k;
-            double R = site_rate_sum(a.g, a.P, i, j, k, nullptr);
-            double dep = 0.0;
-            bool has_dep = false;
-            if (i == L - 1 && vox_state(a.g.vox[s]) == 0) {
-                has_dep = dep_rate(a.P, a.g.T[s], &dep);
-                if (has_dep) R = dep + R;
-            }
-            rsum += R;
-            rmax = fmax(rmax, R);
-            if (!(R > 0.0) || !(tau > 0.0)) continue;
+        RowLists lists;
+        lists.occ = (uint16_t *)(dyn_smem + (size_t)w * 2 * L * sizeof(uint16_t));
+        lists.emp = lists.occ + L;
+        row_classify(a.g, a.P, rbase, lists, nullptr);
+        // one site: accumulate the totals, draw, and (rarely) fire
+        auto visit = [&](int k, double R, bool has_dep, double dep, bool active) {
+            bool fire = false;
+            double u_pick = 0.0;
             const long long gsite = (long long)i * LL + (long long)j * L + k;
-            double u_fire, u_pick;
-            philox_u2(a.seed, (uint64_t)gsite, a.sweep, 0u, &u_fire, &u_pick);
-            const double pfire = -expm1(-R * tau);
-            if (!(u_fire < pfire)) continue;
-            // pick one event with probability rate / R (list order: dep, then the site's events)
-            const double x = u_pick * R;
-            double cum = 0.0;
-            int ety = -1, eslot = -1, eatom = 0;
-            bool found = false;
-            if (has_dep) {
-                cum = dep; ety = CET_EV_DEP; eatom = a.P.states_w;
-                if (cum >= x) found = true;
-            }
-            if (!found)
-                site_events(a.g, a.P, i, j, k, [&](int ty, int slot, double rate, int atom) {
-                    if (found) return;
-                    cum += rate; ety = ty; eslot = slot; eatom = atom;
-                    if (cum >= x) found = true;
-                });
-            if (ety < 0) continue;
-            Record rec;
-            rec.src = s;
-            rec.theta = 0.0; rec.phi = 0.0;
-            int64_t tgt = -1;
-            if (ety == CET_EV_DEP || ety == CET_EV_NUC) {
-                double ut, up;
-                philox_u2(a.seed, (uint64_t)gsite, a.sweep, 1u, &ut, &up);
-                rec.theta = __dmul_rn(3.141592653589793, ut);          // np.random.uniform(0, pi)
-                rec.phi = __dmul_rn(2 * 3.141592653589793, up);        // np.random.uniform(0, 2pi)
-                if (ety == CET_EV_DEP) {                               // kmc_event_rates.py:65-71
-                    double us, unused;
-                    philox_u2(a.seed, (uint64_t)gsite, a.sweep, 2u, &us, &unused);
-                    eatom = dep_species(a.P, us);
+            if (active) {
+                rsum += R;
+                rmax = fmax(rmax, R);
+                if (R > 0.0 && tau > 0.0) {
+                    double u_fire;
+                    philox_u2(a.seed, (uint64_t)gsite, a.sweep, 0u, &u_fire, &u_pick);
+                    const double x = R * tau;                 // 1 - exp(-x) <= x: most sites reject here
+                    if (u_fire < x) fire = u_fire < -expm1(-x);
                 }
-            } else {
-                tgt = s + CET_NB_DI(eslot) * LL + CET_NB_DJ(eslot) * L + CET_NB_DK(eslot);
-                if (ety == CET_EV_ATT) { rec.theta = a.g.theta[tgt]; rec.phi = a.g.phi[tgt]; }
-                else { rec.theta = a.g.theta[s]; rec.phi = a.g.phi[s]; }
             }
-            const int rank = colour_rank(i, j, k, a.sweep);
-            rec.info = ety | ((eslot + 1) << 4) | (eatom << 12);
-            rec.colour_rank = rank;
-            const unsigned int slot = atomicAdd(&a.ss->n_records, 1u);
-            if (slot >= a.cap_records) { a.ss->overflow = 1; continue; }
-            const unsigned long long key = claim_key(rank, gsite);
-            atomicMax(&a.claim[s], key);
-            if (ety == CET_EV_DIFF) atomicMax(&a.claim[tgt], key);
-            a.records[slot] = rec;
-        }
+            if (fire) fire_event(a, i, j, k, rbase + k, gsite, R, dep, has_dep, u_pick);
+            __syncwarp();      // re-converge before the next chunk (keeps the dense part 32-wide)
+        };
+        row_occupied(a.g, a.P, i, j, rbase, lists,
+                     [&](int k, double sum, bool active) { visit(k, sum, false, 0.0, active); });
+        row_empty(a.g, a.P, i, j, rbase, lists, [&](int k, double sum, bool has_dep, double dep, bool active) {
+            visit(k, has_dep ? dep + sum : sum, has_dep, dep, active);
+        });
     }
     rsum = warp_sum(rsum);
     rmax = warp_max(rmax);
@@ -222,7 +245,7 @@ __global__ void sweep_finalize_kernel(SweepState *ss, const double *plane_sum, i
 
 struct ApplyArgs {
     uint8_t *vox;
-    double *theta, *phi;
+    double *theta, *phi, *vx, *vy, *vz;
     SweepState *ss;
     const Record *records;
     unsigned int cap_records;
@@ -262,15 +285,20 @@ __global__ void sweep_apply_kernel(const ApplyArgs a)
         const bool win = complete && cs == key && ct == key;
         if (win) {
             int64_t upd = s;
+            double ux, uy, uz;
+            unit_vector(rec.theta, rec.phi, &ux, &uy, &uz);          // same bits as the source's resident vector
             if (ety == CET_EV_DIFF) {                                    // kmc_simulation.py:292-303
                 a.vox[tgt] = (uint8_t)((a.vox[tgt] & 0xF0) | (a.vox[s] & 0x0F));
                 a.theta[tgt] = rec.theta; a.phi[tgt] = rec.phi;
+                a.vx[tgt] = ux; a.vy[tgt] = uy; a.vz[tgt] = uz;
                 a.vox[s] = (uint8_t)(a.vox[s] & 0xF0);
                 a.theta[s] = 0.0; a.phi[s] = 0.0;
+                a.vx[s] = 0.0; a.vy[s] = 0.0; a.vz[s] = 1.0;
                 upd = tgt;
             } else {                                                     // dep / nuc / att
                 a.vox[s] = (uint8_t)((a.vox[s] & 0xF0) | eatom);
                 a.theta[s] = rec.theta; a.phi[s] = rec.phi;
+                a.vx[s] = ux; a.vy[s] = uy; a.vz[s] = uz;
                 if (ety == CET_EV_NUC && owned) ++nuc;
             }
             if (a.defect_fraction > 0.0) {                               // :323-327
@@ -279,6 +307,7 @@ __global__ void sweep_apply_kernel(const ApplyArgs a)
                 if (u2 < a.defect_fraction) {
                     a.vox[upd] = (uint8_t)((a.vox[upd] & 0xF0) | a.P.defect_id);
                     a.theta[upd] = 0.0; a.phi[upd] = 0.0;
+                    a.vx[upd] = 0.0; a.vy[upd] = 0.0; a.vz[upd] = 1.0;
                 }
             }
             if (owned) ++applied;
@@ -373,12 +402,18 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
     const int n_eval = R.eval_hi - R.eval_lo;
     const int i_off = (int)(c->i_begin - c->halo);
     double *max_slot = c->plane_sum + c->n0;      // plane_sum[n0] holds the running max
+    CET_REQUIRE(c->n1 <= 65535, "cet_sweep_run: L must fit 16-bit row indices");
+    const size_t decide_smem = (size_t)SW_WARPS * 2 * c->n1 * sizeof(uint16_t);
+    if (decide_smem > 48 * 1024)
+        CET_CUDA(cudaFuncSetAttribute(sweep_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)decide_smem));
 
     SweepState before;
     CET_CUDA(cudaMemcpyAsync(&before, c->sweep, sizeof(before), cudaMemcpyDeviceToHost, c->stream));
     CET_CUDA(cudaStreamSynchronize(c->stream));
 
     for (int64_t n = 0; n < n_sweeps; ++n) {
+        ProfScope step_scope(c, PROF_STEP);
         if (sp->thermal_every > 0 && c->sweep_index % sp->thermal_every == 0) {
             if (int rc = thermal_cet_step(c, tp, &c->sweep->terminated)) return rc;
             if (c->world > 1) if (int rc = comm_halo_exchange(c, 4)) return rc;
@@ -386,13 +421,16 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
         sweep_reset_kernel<<<1, 1, 0, c->stream>>>(c->sweep, max_slot);
         CET_CUDA(cudaMemsetAsync(c->plane_sum, 0, (size_t)c->n0 * sizeof(double), c->stream));
         SweepArgs a;
-        a.g = c->lat(); a.P = c->rp; a.ss = c->sweep;
+        a.g = c->lat(); a.theta = c->theta; a.phi = c->phi; a.P = c->rp; a.ss = c->sweep;
         a.records = (Record *)c->records; a.cap_records = (unsigned int)c->cap_records;
         a.claim = c->claim; a.blk_sum = c->blk_sum; a.blk_max = c->blk_max;
         a.p_lo = R.eval_lo; a.p_hi = R.eval_hi; a.np = (int)c->np;
         a.seed = sp->seed; a.sweep = (uint32_t)c->sweep_index;
         a.rows_per_blk = SW_WARPS; a.blks_per_plane = bpp;
-        sweep_decide_kernel<<<n_eval * bpp, SW_WARPS * 32, 0, c->stream>>>(a);
+        {
+            ProfScope ps(c, PROF_DECIDE);
+            sweep_decide_kernel<<<n_eval * bpp, SW_WARPS * 32, decide_smem, c->stream>>>(a);
+        }
         CET_CUDA(cudaGetLastError());
         sweep_plane_reduce_kernel<<<(n_eval + 3) / 4, 128, 0, c->stream>>>(
             c->blk_sum, c->blk_max, bpp, n_eval, i_off + R.eval_lo, (int)c->i_begin, (int)c->i_end,
@@ -400,17 +438,24 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
         CET_CUDA(cudaGetLastError());
         if (c->world > 1) if (int rc = comm_sweep_reduce(c, c->plane_sum, (int)c->n0, max_slot)) return rc;
         ApplyArgs b;
-        b.vox = c->vox; b.theta = c->theta; b.phi = c->phi; b.ss = c->sweep;
+        b.vox = c->vox; b.theta = c->theta; b.phi = c->phi; b.vx = c->vx; b.vy = c->vy; b.vz = c->vz;
+        b.ss = c->sweep;
         b.records = (const Record *)c->records; b.cap_records = (unsigned int)c->cap_records;
         b.claim = c->claim; b.P = c->rp; b.L = (int)c->n1; b.i_off = i_off;
         b.c_lo = R.claim_lo; b.c_hi = R.claim_hi; b.own_lo = R.own_lo; b.own_hi = R.own_hi;
         b.seed = sp->seed; b.sweep = (uint32_t)c->sweep_index; b.defect_fraction = sp->defect_fraction;
-        sweep_apply_kernel<<<148 * 4, 256, 0, c->stream>>>(b);
+        {
+            ProfScope ps(c, PROF_APPLY);
+            sweep_apply_kernel<<<148 * 4, 256, 0, c->stream>>>(b);
+        }
         CET_CUDA(cudaGetLastError());
         sweep_finalize_kernel<<<1, 256, 0, c->stream>>>(c->sweep, c->plane_sum, (int)c->n0, max_slot,
                                                         sp->events_per_sweep, sp->p_max);
         CET_CUDA(cudaGetLastError());
-        if (c->world > 1) if (int rc = comm_halo_exchange(c, 1 | 2)) return rc;
+        if (c->world > 1) {
+            ProfScope ps(c, PROF_HALO);
+            if (int rc = comm_halo_exchange(c, 1 | 2)) return rc;
+        }
         c->sweep_index++;
     }
     c->rates_valid = false;

@@ -138,7 +138,10 @@ static int launch_thermal(cet_ctx *c, ThermalArgs &a)
     dim3 block(TH_TK, TH_TJ);
     dim3 grid((unsigned)((c->n2 + TH_TK - 1) / TH_TK), (unsigned)((c->n1 + TH_TJ - 1) / TH_TJ),
               (unsigned)((a.p_hi - a.p_lo + TH_PLANES - 1) / TH_PLANES));
-    thermal_kernel<FULL><<<grid, block, 0, c->stream>>>(a);
+    {
+        ProfScope ps(c, PROF_THERMAL);
+        thermal_kernel<FULL><<<grid, block, 0, c->stream>>>(a);
+    }
     CET_CUDA(cudaGetLastError());
     // planes outside [p_lo, p_hi) keep their previous contents: copy them so that the swap
     // below does not resurrect values from two steps ago in ghost planes.

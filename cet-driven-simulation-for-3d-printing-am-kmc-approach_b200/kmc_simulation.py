@@ -206,10 +206,24 @@ def slab_bounds(L: int, world: int, rank: int):
 SWEEP_HALO = 6       # ghost planes per side a slab needs for one communication per sweep
 
 
+def run_kmc_sublattice_slab(ctx, packed, theta, phi, T, n_sweeps, sweep_params, thermal=None):
+    """One call = upload this rank's planes from host memory (packed uint8 state | defects << 4,
+    float64 theta / phi / T), refresh the ghost planes, run n_sweeps synchronous-sublattice
+    sweeps, and read the lattice back.  `ctx` is an existing cetkmc.Context (already bound to its
+    communicator when the lattice spans several GPUs)."""
+    ctx.upload_packed(packed)
+    ctx.upload(theta=theta, phi=phi, T=T)
+    ctx.halo_exchange(7)
+    out = ctx.sweep_run(n_sweeps, sweep_params, thermal)
+    out["packed"] = ctx.download_packed()
+    out.update(ctx.download(theta=True, phi=True))
+    return out
+
+
 def run_kmc_sublattice(state, theta, phi, T, defects_mask=None, n_sweeps=100, impurity_c=0.0,
                        defect_fraction=0.0, seed=None, events_per_sweep=None, p_max=0.25,
                        thermal_every=THERMAL_EVERY, device=0, rank=0, world=1, unique_id=None,
-                       return_fields=True):
+                       return_fields=True, packed=False):
     """Synchronous-sublattice KMC on a lattice resident in HBM (see csrc/sweep.cu).
 
     state/theta/phi/T/defects_mask are the FULL (L,L,L) arrays in the reference layout (or, when
@@ -217,6 +231,10 @@ def run_kmc_sublattice(state, theta, phi, T, defects_mask=None, n_sweeps=100, im
     taken from the neighbours — pass full arrays and the slicing is done here).  Every rank of a
     multi-GPU run calls this with the same arguments plus its rank and the shared NCCL
     `unique_id` (cetkmc._lib.comm_unique_id() created on rank 0).
+
+    packed=True: `state` is the one-byte-per-voxel form (uint8, state | defects_mask << 4) and the
+    result carries `packed` instead of the int64 state / atom_type arrays — 1 B instead of 24 B per
+    voxel across PCIe.
 
     Returns a dict: counters of the run and, if return_fields, the rank's owned planes of
     state / atom_type / theta / phi / T.
@@ -229,8 +247,12 @@ def run_kmc_sublattice(state, theta, phi, T, defects_mask=None, n_sweeps=100, im
     try:
         ctx.set_rate_params(rate_params(impurity_c, 1, 2, 3))
         own = slice(i_begin, i_end)
-        ctx.upload(state=state[own], theta=theta[own], phi=phi[own], T=T[own],
-                   defects=None if defects_mask is None else defects_mask[own])
+        if packed:
+            ctx.upload_packed(state[own])
+            ctx.upload(theta=theta[own], phi=phi[own], T=T[own])
+        else:
+            ctx.upload(state=state[own], theta=theta[own], phi=phi[own], T=T[own],
+                       defects=None if defects_mask is None else defects_mask[own])
         if world > 1:
             if unique_id is None:
                 raise ValueError("world > 1 needs the NCCL unique id created on rank 0")
@@ -245,7 +267,10 @@ def run_kmc_sublattice(state, theta, phi, T, defects_mask=None, n_sweeps=100, im
         tp = thermal_params(THERMAL_DT, nan_to_num=True) if thermal_every > 0 else None
         out = ctx.sweep_run(n_sweeps, sp, tp)
         out["i_begin"], out["i_end"] = i_begin, i_end
-        if return_fields:
+        if return_fields and packed:
+            out["packed"] = ctx.download_packed()
+            out.update(ctx.download(theta=True, phi=True, T=True))
+        elif return_fields:
             out.update(ctx.download(state=True, atom_type=True, theta=True, phi=True, T=True))
         return out
     finally:

@@ -102,6 +102,10 @@ int cet_device_name(int device, char *buf, int buflen);
  * on each side (single GPU: i_begin=0, i_end=L, halo=0).  For thermal-only use the lattice
  * may be non-cubic: cet_create_shape(n0, n1, n2). */
 int cet_create(cet_ctx **ctx, int device, int64_t L, int64_t i_begin, int64_t i_end, int32_t halo);
+/* Same with n0 planes along axis 0 and L x L sites per plane (n0 == L is the reference's cubic
+ * lattice; n0 > L stacks slabs for weak scaling over several GPUs). */
+int cet_create_slab(cet_ctx **ctx, int device, int64_t n0, int64_t L, int64_t i_begin, int64_t i_end,
+                    int32_t halo);
 int cet_create_shape(cet_ctx **ctx, int device, int64_t n0, int64_t n1, int64_t n2);
 int cet_destroy(cet_ctx *ctx);
 int cet_sync(cet_ctx *ctx);
@@ -120,7 +124,7 @@ int cet_snapshot_state(cet_ctx *ctx); /* prev_state := state, on device */
 int cet_upload_packed(cet_ctx *ctx, const uint8_t *packed);
 int cet_download_packed(cet_ctx *ctx, uint8_t *packed);
 /* Raw device pointers for tensor hand-off (torch.distributed halo exchange, tests).
- * which: 0 packed state, 1 theta, 2 phi, 3 T, 4 site_rate.  Pointer addresses local plane 0
+ * which: 0 packed state, 1 theta, 2 phi, 3 T, 4 site_rate, 5/6/7 orientation unit vector x/y/z.  Pointer addresses local plane 0
  * (ghost planes included); nbytes is the full extent. */
 int cet_device_ptr(cet_ctx *ctx, int which, void **ptr, int64_t *nbytes);
 int cet_counts(cet_ctx *ctx, int64_t counts[16]); /* histogram of state values, owned planes */
@@ -170,6 +174,12 @@ int cet_comm_destroy(cet_ctx *ctx);
 /* fields bitmask: 1 state, 2 theta+phi, 4 T */
 int cet_halo_exchange(cet_ctx *ctx, int fields);
 int cet_allreduce_f64(cet_ctx *ctx, double *inout_host, int n, int op /* 0 sum, 1 max */);
+
+/* ---- per-kernel device timing: CUDA event pairs recorded on the context stream around every
+ * launch of a kind while enabled.  kind: 0 sweep decide, 1 sweep apply, 2 thermal stencil,
+ * 3 dense rate kernel, 4 halo exchange, 5 whole sweep. */
+int cet_profile_enable(cet_ctx *ctx, int on);
+int cet_profile_read(cet_ctx *ctx, int kind, double *ms_total, int64_t *launches, int reset);
 
 /* ---- timing helper: elapsed ms of the last N kernels of a kind (CUDA events on the ctx stream) */
 int cet_timer_begin(cet_ctx *ctx);
