@@ -4,9 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cetkmc|reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-One step = one synchronous-sublattice sweep over the whole lattice: thermal stencil when due
-(every 20 sweeps, kmc_simulation.py:248), dense rate evaluation + event decision for every site,
-conflict resolution + apply, totals for the next time increment, and (N > 1) the halo exchange.
+One step = one synchronous-sublattice sweep over the whole lattice (csrc/sweep.cu): thermal stencil
++ dense rate rebuild when due (every 20 sweeps, kmc_simulation.py:248), one fire decision per site
+against its resident rate sum, event pick + conflict resolution + apply for the fired sites,
+neighbour-rate refresh of the sites the events touched, totals for the next time increment, and
+(N > 1) the halo exchange.
 Workload: the 'half-grown' synthetic lattice of SURVEY §8(d)(ii), 512 x 512 x 512 sites per GPU;
 N GPUs hold a (512 N) x 512 x 512 lattice split into z-slabs (weak scaling).
 
@@ -29,9 +31,13 @@ sys.path.insert(0, ROOT)
 
 L_BENCH = 512
 THERMAL_EVERY = 20
-EVENTS_FRACTION = 0.02          # events_per_sweep = 2 % of the sites
-P_MAX = 0.25
-BYTES_PER_SITE_DECIDE = 33      # 1 B state + 8 B T + 24 B unit vector, each read once
+EVENTS_FRACTION = 0.005         # events_per_sweep = 0.5 % of the sites (the level-3 parity tests run at <= this)
+P_MAX = 0.1
+# algorithmic bytes per unit of each dense kernel
+BYTES_STREAM = 8                # resident rate sum read once per site
+BYTES_RATES = 41                # 1 B state + 8 B T + 24 B unit vector read, 8 B rate sum written
+BYTES_STAMP = 4                 # refresh scan: one stamp per site
+BYTES_THERMAL = 16              # T read + T written
 CPU_SAMPLE_L = 160              # cpu_baseline / reference arm: one 160^3 block of the same workload
 
 
@@ -99,7 +105,6 @@ def cpu_rate_sample(threads):
     packed, th, ph, T = _synth.half_grown(Ls, seed=1234)
     st, df = _synth.unpack(packed)
     p = O.make_params(0.1)
-    O.site_rates(st[:8], th[:8], ph[:8], T[:8], df[:8], Ls, p) if False else None
     t0 = time.perf_counter()
     reps = 0
     while True:
@@ -235,37 +240,58 @@ def main():
         events = float(ev.item())
     else:
         events = float(res["events_applied"])
-    decide_ms, decide_n = ctx.profile_read("decide")
-    apply_ms, _ = ctx.profile_read("apply")
-    thermal_ms, thermal_n = ctx.profile_read("thermal")
-    halo_ms, _ = ctx.profile_read("halo")
+    prof = {k: ctx.profile_read(k) for k in ("decide", "pick", "apply", "refresh", "thermal", "rates", "halo")}
     value = sites_total * args.steps / (ms * 1e-3)
     peak, peak_kind = peaks()
-    # the decide kernel also evaluates the ghost planes it needs (N > 1): count what it processed
+    # planes a dense kernel processes: the owned planes plus the ghost planes it must evaluate (N > 1)
     eval_planes = (i_end - i_begin) + (0 if world == 1 else (4 if rank in (0, world - 1) else 8))
-    achieved = BYTES_PER_SITE_DECIDE * eval_planes * L * L / (decide_ms / max(decide_n, 1) * 1e-3) / 1e9
+    eval_sites = eval_planes * L * L
+
+    def roof(kind, nbytes):
+        t_ms, n = prof[kind]
+        if n == 0 or t_ms <= 0:
+            return None
+        ach = nbytes / (t_ms / n * 1e-3) / 1e9
+        return {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "launches": int(n),
+                "ms_per_launch": t_ms / n, "bytes_per_launch": nbytes}
+
+    refreshed = res["sites_refreshed"] / max(args.steps, 1)
+    rl = {
+        "sweep_stream_kernel": roof("decide", BYTES_STREAM * eval_sites),
+        "dirty_scan+dirty_eval (neighbour-rate refresh)": roof("refresh", BYTES_RATES * refreshed + BYTES_STAMP * eval_sites),
+        "rates_rows_kernel (dense rebuild after the thermal step)": roof("rates", BYTES_RATES * eval_sites),
+        "thermal_kernel": roof("thermal", BYTES_THERMAL * (i_end - i_begin) * L * L),
+    }
+    share = {k: prof[k][0] for k in ("decide", "pick", "apply", "refresh", "thermal", "rates", "halo")}
+    dominant = max(share, key=share.get)
+    dom_name = {"decide": "sweep_stream_kernel", "refresh": "dirty_scan+dirty_eval (neighbour-rate refresh)",
+                "rates": "rates_rows_kernel (dense rebuild after the thermal step)", "thermal": "thermal_kernel"}.get(dominant)
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "decide_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(dominant)
     except Exception:
         pass
+    main_roof = dict(rl[dom_name]) if dom_name and rl.get(dom_name) else {"achieved": None, "peak": peak, "unit": "GB/s", "frac": None}
+    main_roof.update({"bound": "hbm", "kernel": dom_name or dominant, "traffic": traffic, "peak_kind": peak_kind,
+                      "share_of_step": share[dominant] / max(sum(share.values()), 1e-9)})
+    n_rates = prof["rates"][1]
     out = {
         "metric": "kmc_site_updates_per_s", "value": value, "unit": "site-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"half-grown lattice {n0}x{L}x{L} (SURVEY 8d-ii: 25% solid, salt-and-pepper below a "
-                               f"wavy front, linear G), {L} planes per GPU, sublattice sweeps, thermal stencil every "
-                               f"{THERMAL_EVERY} sweeps, events_per_sweep={EVENTS_FRACTION:.2f}N, p_max={P_MAX}",
-                   "l2": "per-sweep inputs (4.4 GB) exceed the 126 MB L2; no flush needed",
+                               f"wavy front, linear G), {L} planes per GPU, synchronous-sublattice sweeps with resident "
+                               f"rates + neighbour-rate refresh, thermal stencil and dense rate rebuild every "
+                               f"{THERMAL_EVERY} sweeps, events_per_sweep={EVENTS_FRACTION}N, p_max={P_MAX}",
+                   "l2": "fields swept per step (>= 1 GB rate sums, 0.5 GB stamps) exceed the 126 MB L2; no flush needed",
                    "parallelism": f"zslab{world}"},
         "executed_events_per_s": events / (ms * 1e-3),
-        "kernel_ms_per_step": {"decide": decide_ms / args.steps, "apply": apply_ms / args.steps,
-                               "thermal": thermal_ms / args.steps, "halo": halo_ms / args.steps},
-        "roofline": {"bound": "hbm", "kernel": "sweep_decide_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
-                     "bytes_per_site": BYTES_PER_SITE_DECIDE},
-        "gpu_launches": int(5 * args.steps + thermal_n),
+        "kernel_ms_per_step": {k: v / args.steps for k, v in share.items()},
+        "roofline": main_roof,
+        "roofline_all": rl,
+        # per sweep: reset, stream, plane-reduce, pick, apply, dirty-scan, dirty-eval, finalize
+        "gpu_launches": int(8 * args.steps + prof["thermal"][1] + n_rates),
         "clocks": clocks,
     }
 

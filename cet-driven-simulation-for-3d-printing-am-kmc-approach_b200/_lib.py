@@ -60,7 +60,7 @@ class SweepResult(C.Structure):                     # cet_sweep_result
                 ("events_applied", C.c_int64), ("nucleation_count", C.c_int64),
                 ("sweep_index", C.c_int64), ("time", C.c_double), ("last_total_rate", C.c_double),
                 ("last_max_rate", C.c_double), ("last_tau", C.c_double),
-                ("terminated", C.c_int32), ("overflow", C.c_int32)]
+                ("terminated", C.c_int32), ("overflow", C.c_int32), ("sites_refreshed", C.c_int64)]
 
 
 _lib = None
@@ -375,7 +375,7 @@ class Context:
         check(lib().cet_sweep_reset(self._h), "cet_sweep_reset")
 
     # -- timing -----------------------------------------------------------------------------
-    PROF_KINDS = dict(decide=0, apply=1, thermal=2, rates=3, halo=4, step=5)
+    PROF_KINDS = dict(decide=0, apply=1, thermal=2, rates=3, halo=4, step=5, pick=6, refresh=7)
 
     def profile_enable(self, on=True):
         check(lib().cet_profile_enable(self._h, 1 if on else 0), "cet_profile_enable")

@@ -214,7 +214,7 @@ int cet_destroy(cet_ctx *c)
     void *ptrs[] = {c->vox, c->vox_prev, c->theta, c->phi, c->vx, c->vy, c->vz, c->T, c->T2, c->site_rate, c->dep_rate,
                     c->row_occ, c->row_emp, c->row_dep, c->row_depcnt, c->seg, c->total, c->q_top,
                     c->stage, c->kmc, c->d_py, c->d_np, c->d_sp, c->d_log, c->sweep, c->claim,
-                    c->records, c->blk_sum, c->blk_max, c->plane_sum};
+                    c->records, c->blk_sum, c->blk_max, c->plane_sum, c->stamp, c->dirty, c->fired};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &sp : c->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -242,7 +242,7 @@ int cet_set_rate_params(cet_ctx *c, const cet_rate_params *p)
                 "cet_set_rate_params: species ids must be in 1..15");
     c->rp = *p;
     c->have_rp = true;
-    c->rates_valid = false;
+    c->rates_valid = false; c->sweep_rates_valid = false;
     return 0;
 }
 
@@ -277,7 +277,7 @@ int cet_upload(cet_ctx *c, const int64_t *state, const double *theta, const doub
     }
     if (theta || phi) if (int rc = orient_update(c, c->halo, c->np - c->halo)) return rc;
     CET_CUDA(cudaStreamSynchronize(c->stream));
-    c->rates_valid = false;
+    c->rates_valid = false; c->sweep_rates_valid = false;
     return 0;
 }
 
@@ -345,7 +345,7 @@ int cet_upload_packed(cet_ctx *c, const uint8_t *packed)
     CET_CUDA(cudaMemcpyAsync(c->vox + c->owned_offset(), packed, (size_t)c->owned_sites(),
                              cudaMemcpyHostToDevice, c->stream));
     CET_CUDA(cudaStreamSynchronize(c->stream));
-    c->rates_valid = false;
+    c->rates_valid = false; c->sweep_rates_valid = false;
     return 0;
 }
 

@@ -38,8 +38,11 @@ struct KmcState {
 };
 
 struct SweepState {
-    unsigned long long n_fired, n_applied, n_nuc;   // running totals (device atomics)
-    unsigned int n_records, overflow;               // records appended by the current sweep
+    unsigned long long n_fired_total, n_applied, n_nuc;   // running totals over owned sites (device atomics)
+    unsigned long long n_refreshed_total;                 // sites re-evaluated by the neighbour-rate refresh
+    unsigned int n_fired;                           // fired-site list length of the current sweep
+    unsigned int n_dirty, n_dirty_emp;              // refresh lists (occupied, empty) — adjacent: one pointer
+    unsigned int overflow, dirty_overflow, pad0_;   // the fired list overflowed (events dropped)
     double sum_rate, max_rate;                      // totals of the rates seen by the last sweep
     double tau, time;                               // interval of the next sweep; accumulated time
     int32_t terminated, pad_;
@@ -81,7 +84,8 @@ struct cet_ctx {
     int32_t *row_depcnt = nullptr;
     double *total = nullptr;          // [0] total, [1] (as int64) n_dep
     double *q_top = nullptr;
-    bool rates_valid = false;
+    bool rates_valid = false;         // site_rate / dep_rate and the BKL sum hierarchy valid on the owned planes
+    bool sweep_rates_valid = false;   // site_rate / dep_rate valid on the planes the sweep evaluates
 
     // staging for host<->device conversion (grown on demand)
     void *stage = nullptr;
@@ -98,6 +102,9 @@ struct cet_ctx {
     size_t cap_log = 0;
 
     // sweep mode
+    uint32_t *stamp = nullptr;        // per site: sweep id of the last refresh request (dedups the dirty list)
+    int32_t *dirty = nullptr, *fired = nullptr;
+    size_t cap_dirty = 0, cap_fired = 0;
     cet::SweepState *sweep = nullptr;
     unsigned long long *claim = nullptr;
     void *records = nullptr;
@@ -132,7 +139,8 @@ struct cet_ctx {
 namespace cet {
 int ensure_stage(cet_ctx *c, size_t bytes);
 int orient_update(cet_ctx *c, int64_t p_lo, int64_t p_hi);   // v := unit_vector(theta, phi) on local planes
-enum { PROF_DECIDE = 0, PROF_APPLY = 1, PROF_THERMAL = 2, PROF_RATES = 3, PROF_HALO = 4, PROF_STEP = 5, PROF_KINDS = 6 };
+enum { PROF_DECIDE = 0, PROF_APPLY = 1, PROF_THERMAL = 2, PROF_RATES = 3, PROF_HALO = 4, PROF_STEP = 5, PROF_PICK = 6,
+       PROF_REFRESH = 7, PROF_KINDS = 8 };
 // RAII span: records an event pair around a launch when profiling is on.
 struct ProfScope {
     cet_ctx *c; int kind; cudaEvent_t a = nullptr;

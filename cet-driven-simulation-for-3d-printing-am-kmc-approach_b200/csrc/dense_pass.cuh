@@ -29,17 +29,24 @@ struct RowLists {
 };
 
 // Pass 1: classify the sites of row (p, j).  zero_row (may be NULL) is a per-warp L-entry
-// buffer that is cleared here (defect sites keep rate 0).
-__device__ __forceinline__ void row_classify(const Lat &g, const cet_rate_params &P, int64_t rbase, RowLists &w,
-                                             double *zero_row)
+// buffer that is cleared here (defect sites keep rate 0).  With a stamp array only the sites whose
+// stamp equals stamp_id are listed (neighbour-rate refresh after a sweep); other(k, st) is then
+// called for every selected site that owns no event list entry (defects).
+template <class F>
+__device__ __forceinline__ void row_classify(const Lat &g, const cet_rate_params &P, int rbase, RowLists &w,
+                                             double *zero_row, const uint32_t *stamp, uint32_t stamp_id, F &&other)
 {
     const int L = g.L, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     int n_occ = 0, n_emp = 0;
     for (int k0 = 0; k0 < L; k0 += 32) {
         const int k = k0 + lane;
-        const int st = k < L ? vox_state(g.vox[rbase + k]) : -1;
+        bool sel = k < L;
+        if (stamp != nullptr && sel) sel = stamp[rbase + k] == stamp_id;
+        if (stamp != nullptr && !__any_sync(0xffffffffu, sel)) continue;
+        const int st = sel ? vox_state(g.vox[rbase + k]) : -1;
         const bool is_emp = st == 0, is_occ = st > 0 && st != P.defect_id;
+        if (sel && !is_emp && !is_occ) other(k, st);
         const unsigned me = __ballot_sync(0xffffffffu, is_emp), mo = __ballot_sync(0xffffffffu, is_occ);
         if (is_emp) w.emp[n_emp + __popc(me & lt)] = (uint16_t)k;
         if (is_occ) w.occ[n_occ + __popc(mo & lt)] = (uint16_t)k;
@@ -50,78 +57,134 @@ __device__ __forceinline__ void row_classify(const Lat &g, const cet_rate_params
     __syncwarp();
 }
 
-// Pass 2: occupied sites.  fn(k, rate_sum, active) is called by all 32 lanes of the warp once
-// per chunk (converged), `active` false on the padding lanes of the last chunk.
-template <class F>
-__device__ __forceinline__ void row_occupied(const Lat &g, const cet_rate_params &P, int i, int j, int64_t rbase,
-                                             const RowLists &w, F &&fn)
+// Neighbour offsets as 32-bit linear index deltas, one table per CTA in shared memory (the
+// dense kernels require the local extent to fit 31 bits, checked by the launchers).
+struct NbOffsets { int lin[14]; };
+__device__ __forceinline__ void nb_offsets_init(NbOffsets *t, int L)
 {
-    const int L = g.L, lane = threadIdx.x & 31;
-    const unsigned inb_ij = inbounds_mask_ij(i, j, g.n0, L);
+    if (threadIdx.x < 14)
+        t->lin[threadIdx.x] = ((int)c_nb_off[threadIdx.x][0] * L + c_nb_off[threadIdx.x][1]) * L + c_nb_off[threadIdx.x][2];
+    __syncthreads();
+}
+
+// Neighbour states of site s, 4 bits per slot, split over two 32-bit words (slots 0-7, 8-13) so
+// that the nibble tests below are single 32-bit operations.
+struct Nst { unsigned lo, hi; };
+__device__ __forceinline__ Nst neighbour_states32(const uint8_t *vox, int s, unsigned inb, const NbOffsets *t)
+{
+    Nst n;
+    n.lo = 0; n.hi = 0;
+#pragma unroll 1
+    for (int o = 0; o < 8; ++o)
+        if (inb >> o & 1u) n.lo |= (unsigned)(vox[s + t->lin[o]] & 15) << (4 * o);
+#pragma unroll 1
+    for (int o = 8; o < 14; ++o)
+        if (inb >> o & 1u) n.hi |= (unsigned)(vox[s + t->lin[o]] & 15) << (4 * (o - 8));
+    return n;
+}
+__device__ __forceinline__ unsigned nib_nonzero32(unsigned x) { return (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u; }
+__device__ __forceinline__ unsigned nib_equals32(unsigned x, int v) { return ~nib_nonzero32(x ^ (0x11111111u * (unsigned)v)) & 0x11111111u; }
+// bit o of the result <=> bit 4*o of the nibble-LSB mask pair (lo: slots 0-7, hi: slots 8-13)
+__device__ __forceinline__ bool slot_bit(unsigned lo, unsigned hi, int o)
+{
+    return ((o < 8 ? lo >> (4 * o) : hi >> (4 * (o - 8))) & 1u) != 0;
+}
+
+// One chunk of up to 32 occupied sites, one per lane (warp-collective: all 32 lanes call it;
+// `active` false on padding lanes).  Returns the lane's diffusion-rate sum in slot order.
+__device__ __forceinline__ double occ_chunk(const Lat &g, const cet_rate_params &P, const NbOffsets *nbt, int i, int j,
+                                            int k, int s, bool active)
+{
+    const unsigned inb = inbounds_mask(i, j, k, g.n0, g.L);
+    const Nst nst = neighbour_states32(g.vox, s, inb, nbt);
+    const int n_bonds = __popc(nib_nonzero32(nst.lo)) + __popc(nib_nonzero32(nst.hi));
+    const bool has_events = active && n_bonds != __popc(inb);        // an in-bounds neighbour is empty
+    double sum = 0.0;
+    if (__any_sync(0xffffffffu, has_events)) {
+        const uint8_t v = g.vox[s];
+        OccPrep q;
+        q.local_T = 1.0; q.boltz = 0.0;
+        if (has_events) q = occ_prep(P, vox_state(v), vox_defects(v), g.T[s], n_bonds);
+        unsigned emp_nb = 0;                                          // empty in-bounds neighbours, one bit per slot
+        if (has_events) {
+            const unsigned zl = ~nib_nonzero32(nst.lo) & 0x11111111u, zh = ~nib_nonzero32(nst.hi) & 0x00111111u;
+#pragma unroll 1
+            for (int o = 0; o < 14; ++o)
+                if (slot_bit(zl, zh, o)) emp_nb |= 1u << o;
+            emp_nb &= inb;
+        }
+#pragma unroll 1
+        for (int o = 0; o < 14; ++o) {
+            const bool on = emp_nb >> o & 1u;
+            if (!__any_sync(0xffffffffu, on)) continue;
+            if (on) sum += diff_pair_rate(P, q, g.T[s + nbt->lin[o]]);
+        }
+    }
+    return sum;
+}
+
+// One chunk of up to 32 empty sites.  Returns the nucleation + attachment rate sum in slot order;
+// the deposition event (global top plane only) is reported separately.
+__device__ __forceinline__ double emp_chunk(const Lat &g, const cet_rate_params &P, const NbOffsets *nbt, int i, int j,
+                                            int k, int s, bool active, bool *has_dep, double *dep)
+{
+    const int L = g.L;
+    const unsigned inb = inbounds_mask(i, j, k, g.n0, L);
+    const Nst nst = neighbour_states32(g.vox, s, inb, nbt);
+    const unsigned re_l = nib_equals32(nst.lo, P.states_re), re_h = nib_equals32(nst.hi, P.states_re) & 0x00111111u;
+    const unsigned c_l = nib_equals32(nst.lo, P.states_c), c_h = nib_equals32(nst.hi, P.states_c) & 0x00111111u;
+    unsigned att_l = nib_equals32(nst.lo, P.states_w) | re_l | c_l;           // nibble-LSB set: slot offers an attachment
+    unsigned att_h = (nib_equals32(nst.hi, P.states_w) & 0x00111111u) | re_h | c_h;
+    if (!active) { att_l = 0; att_h = 0; }
+    const int km = k - 1 > 0 ? k - 1 : 0, kp = k + 1 < L - 1 ? k + 1 : L - 1;
+    const double T_self = g.T[s];
+    const EmpPrep q = emp_prep(P, T_self, g.T[s + (km - k)], g.T[s + (kp - k)],
+                               __popc(re_l) + __popc(re_h) + __popc(c_l) + __popc(c_h), __popc(inb));
+    double sum = q.nuc_rate;
+    if (__any_sync(0xffffffffu, (att_l | att_h) != 0)) {
+        const double sx = g.vx[s], sy = g.vy[s], sz = g.vz[s];
+#pragma unroll 1
+        for (int o = 0; o < 14; ++o) {
+            const bool on = slot_bit(att_l, att_h, o);
+            if (!__any_sync(0xffffffffu, on)) continue;
+            if (on) {
+                const int t = s + nbt->lin[o];
+                const int ia = slot_bit(re_l, re_h, o) ? 1 : (slot_bit(c_l, c_h, o) ? 2 : 0);
+                sum += att_pair_rate(P, q, ia, sx, sy, sz, g.vx[t], g.vy[t], g.vz[t]);
+            }
+        }
+    }
+    *dep = 0.0;
+    *has_dep = false;
+    if (i == g.n0 - 1 && active) *has_dep = dep_rate(P, T_self, dep);
+    return sum;
+}
+
+// Pass 2: occupied sites of a row.  fn(k, rate_sum, active) is called by all 32 lanes once per chunk.
+template <class F>
+__device__ __forceinline__ void row_occupied(const Lat &g, const cet_rate_params &P, const NbOffsets *nbt, int i,
+                                             int j, int rbase, const RowLists &w, F &&fn)
+{
+    const int lane = threadIdx.x & 31;
     for (int c0 = 0; c0 < w.n_occ; c0 += 32) {
         const bool active = c0 + lane < w.n_occ;
         const int k = w.occ[active ? c0 + lane : c0];
-        const int64_t s = rbase + k;
-        const unsigned inb = inbounds_mask_k(inb_ij, k, L);
-        const uint64_t nst = neighbour_states(g, s, inb);
-        const int n_bonds = popc64(nib_nonzero(nst));
-        const bool has_events = active && n_bonds != popc32(inb);        // an in-bounds neighbour is empty
-        double sum = 0.0;
-        if (__any_sync(0xffffffffu, has_events)) {
-            const uint8_t v = g.vox[s];
-            OccPrep q;
-            q.local_T = 1.0; q.boltz = 0.0;
-            if (has_events) q = occ_prep(P, vox_state(v), vox_defects(v), g.T[s], n_bonds);
-#pragma unroll 1
-            for (int o = 0; o < 14; ++o) {
-                const bool on = has_events && (inb >> o & 1u) && ((nst >> (4 * o)) & 15) == 0;
-                if (!__any_sync(0xffffffffu, on)) continue;
-                if (on) sum += diff_pair_rate(P, q, g.T[g.nb(s, o)]);
-            }
-        }
-        fn(k, sum, active);
+        fn(k, occ_chunk(g, P, nbt, i, j, k, rbase + k, active), active);
     }
 }
 
-// Pass 3: empty sites.  fn(k, rate_sum, has_dep, dep, active); the deposition event exists only
-// on the global top plane (i == n0-1).
+// Pass 3: empty sites of a row.  fn(k, rate_sum, has_dep, dep, active).
 template <class F>
-__device__ __forceinline__ void row_empty(const Lat &g, const cet_rate_params &P, int i, int j, int64_t rbase,
-                                          const RowLists &w, F &&fn)
+__device__ __forceinline__ void row_empty(const Lat &g, const cet_rate_params &P, const NbOffsets *nbt, int i, int j,
+                                          int rbase, const RowLists &w, F &&fn)
 {
-    const int L = g.L, lane = threadIdx.x & 31;
-    const bool top = i == g.n0 - 1;
-    const unsigned inb_ij = inbounds_mask_ij(i, j, g.n0, L);
+    const int lane = threadIdx.x & 31;
     for (int c0 = 0; c0 < w.n_emp; c0 += 32) {
         const bool active = c0 + lane < w.n_emp;
         const int k = w.emp[active ? c0 + lane : c0];
-        const int64_t s = rbase + k;
-        const unsigned inb = inbounds_mask_k(inb_ij, k, L);
-        const uint64_t nst = neighbour_states(g, s, inb);
-        const uint64_t m_re = nib_equals(nst, P.states_re), m_c = nib_equals(nst, P.states_c);
-        uint64_t att_nb = nib_equals(nst, P.states_w) | m_re | m_c;      // bit 4*o: slot o offers an attachment
-        if (!active) att_nb = 0;
-        const int km = k - 1 > 0 ? k - 1 : 0, kp = k + 1 < L - 1 ? k + 1 : L - 1;
-        const double T_self = g.T[s];
-        const EmpPrep q = emp_prep(P, T_self, g.T[s + (km - k)], g.T[s + (kp - k)], popc64(m_re) + popc64(m_c),
-                                   popc32(inb));
-        double sum = q.nuc_rate;
-        if (__any_sync(0xffffffffu, att_nb != 0)) {
-            const double sx = g.vx[s], sy = g.vy[s], sz = g.vz[s];
-#pragma unroll 1
-            for (int o = 0; o < 14; ++o) {
-                const bool on = (att_nb >> (4 * o)) & 1u;
-                if (!__any_sync(0xffffffffu, on)) continue;
-                if (on) {
-                    const int64_t t = g.nb(s, o);
-                    const int ia = species_index(P, (int)(nst >> (4 * o)) & 15);
-                    sum += att_pair_rate(P, q, ia, sx, sy, sz, g.vx[t], g.vy[t], g.vz[t]);
-                }
-            }
-        }
-        double dep = 0.0;
-        bool has_dep = false;
-        if (top && active) has_dep = dep_rate(P, T_self, &dep);
+        bool has_dep;
+        double dep;
+        const double sum = emp_chunk(g, P, nbt, i, j, k, rbase + k, active, &has_dep, &dep);
         fn(k, sum, has_dep, dep, active);
     }
 }

@@ -28,6 +28,8 @@ struct RatesArgs {
     double *site_rate, *dep_rate, *row_occ, *row_emp, *row_dep;
     int32_t *row_depcnt;
     int p_lo, p_hi;   // local planes to evaluate
+    const uint32_t *stamp;   // DIRTY mode: only sites with stamp == stamp_id are re-evaluated
+    uint32_t stamp_id;
 };
 
 // dynamic shared memory per warp: rate_row[L] doubles, then the two uint16 index lists
@@ -40,14 +42,16 @@ __host__ __device__ inline size_t dense_smem_per_warp(int L, bool with_rates)
 __global__ void __launch_bounds__(RB_WARPS * 32) rates_rows_kernel(const RatesArgs a)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ NbOffsets nbt;
     const int L = a.g.L;
+    nb_offsets_init(&nbt, L);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int row = blockIdx.x * RB_WARPS + wid;
     const int nrows = (a.p_hi - a.p_lo) * L;
     if (row >= nrows) return;
     const int p = a.p_lo + row / L, j = row % L;
     const int i = a.g.i_off + p;
-    const int64_t rbase = ((int64_t)p * L + j) * L;
+    const int rbase = (p * L + j) * L;
     unsigned char *mine = dyn_smem + wid * dense_smem_per_warp(L, true);
     double *rate_row = (double *)mine;
     RowLists w;
@@ -56,11 +60,11 @@ __global__ void __launch_bounds__(RB_WARPS * 32) rates_rows_kernel(const RatesAr
     const bool top = i == a.g.n0 - 1;
     if (top)
         for (int k = lane; k < L; k += 32) a.dep_rate[j * L + k] = NAN;    // empty sites overwrite below
-    row_classify(a.g, a.P, rbase, w, rate_row);
-    row_occupied(a.g, a.P, i, j, rbase, w, [&](int k, double sum, bool active) {
+    row_classify(a.g, a.P, rbase, w, rate_row, nullptr, 0u, [](int, int) {});
+    row_occupied(a.g, a.P, &nbt, i, j, rbase, w, [&](int k, double sum, bool active) {
         if (active) rate_row[k] = sum;
     });
-    row_empty(a.g, a.P, i, j, rbase, w, [&](int k, double sum, bool has_dep, double dep, bool active) {
+    row_empty(a.g, a.P, &nbt, i, j, rbase, w, [&](int k, double sum, bool has_dep, double dep, bool active) {
         if (active) {
             rate_row[k] = sum;
             if (has_dep) a.dep_rate[j * L + k] = dep;
@@ -75,6 +79,98 @@ __global__ void __launch_bounds__(RB_WARPS * 32) rates_rows_kernel(const RatesAr
         double ds; int dc;
         warp_dep_row(a.dep_rate + j * L, L, &ds, &dc);
         if (lane == 0) { a.row_dep[j] = ds; a.row_depcnt[j] = dc; }
+    }
+}
+
+// Neighbour-rate refresh (sweep.cu): the sites stamped in this sweep are re-evaluated with the same
+// chunk arithmetic as the dense pass.  Two kernels:
+//   scan  streams the stamp array (4 B/site), compacts the stamped sites of each class into two
+//         global lists (one atomic per class per 8-row tile, so a list stays in lattice order and a
+//         chunk of 32 entries touches a handful of adjacent rows), and settles the sites that own
+//         no list entry (defects; occupied sites of the top plane lose their deposition event);
+//   eval  evaluates the lists 32 sites per warp with every warp of the GPU busy.
+// Results go straight to site_rate / dep_rate; the BKL row sums are not maintained.
+struct DirtyArgs {
+    Lat g;
+    cet_rate_params P;
+    double *site_rate, *dep_rate;
+    const uint32_t *stamp;
+    uint32_t stamp_id;
+    int p_lo, p_hi;
+    int32_t *list_occ, *list_emp;     // capacity: one entry per local site
+    unsigned int *n_occ, *n_emp;      // list lengths (device counters)
+};
+
+__global__ void __launch_bounds__(RB_WARPS * 32) dirty_scan_kernel(const __grid_constant__ DirtyArgs a)
+{
+    __shared__ int s_occ[RB_WARPS * 64], s_emp[RB_WARPS * 64];     // staging; spills are appended directly
+    __shared__ unsigned int c_occ, c_emp, b_occ, b_emp;
+    const int L = a.g.L;
+    if (threadIdx.x == 0) { c_occ = 0; c_emp = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nrows = (a.p_hi - a.p_lo) * L;
+    const int row = blockIdx.x * RB_WARPS + wid;
+    if (row < nrows) {
+        const int p = a.p_lo + row / L, j = row % L;
+        const bool top = a.g.i_off + p == a.g.n0 - 1;
+        const int rbase = (p * L + j) * L;
+        for (int k0 = 0; k0 < L; k0 += 32) {
+            const int k = k0 + lane;
+            const bool sel = k < L && a.stamp[rbase + k] == a.stamp_id;
+            if (!sel) continue;
+            const int st = vox_state(a.g.vox[rbase + k]);
+            if (st != 0) {
+                if (top) a.dep_rate[j * L + k] = NAN;                   // occupied: no deposition event
+                if (st == a.P.defect_id) { a.site_rate[rbase + k] = 0.0; continue; }   // defect: no events
+                const unsigned int q = atomicAdd(&c_occ, 1u);
+                if (q < RB_WARPS * 64) s_occ[q] = rbase + k;
+                else a.list_occ[atomicAdd(a.n_occ, 1u)] = rbase + k;
+            } else {
+                const unsigned int q = atomicAdd(&c_emp, 1u);
+                if (q < RB_WARPS * 64) s_emp[q] = rbase + k;
+                else a.list_emp[atomicAdd(a.n_emp, 1u)] = rbase + k;
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned int no = min(c_occ, (unsigned)(RB_WARPS * 64)), ne = min(c_emp, (unsigned)(RB_WARPS * 64));
+    if (threadIdx.x == 0) {
+        b_occ = no ? atomicAdd(a.n_occ, no) : 0u;
+        b_emp = ne ? atomicAdd(a.n_emp, ne) : 0u;
+    }
+    __syncthreads();
+    for (unsigned int q = threadIdx.x; q < no; q += RB_WARPS * 32) a.list_occ[b_occ + q] = s_occ[q];
+    for (unsigned int q = threadIdx.x; q < ne; q += RB_WARPS * 32) a.list_emp[b_emp + q] = s_emp[q];
+}
+
+__global__ void __launch_bounds__(RB_WARPS * 32) dirty_eval_kernel(const __grid_constant__ DirtyArgs a)
+{
+    __shared__ NbOffsets nbt;
+    const int L = a.g.L, LL = L * L;
+    nb_offsets_init(&nbt, L);
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * RB_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * RB_WARPS;
+    const int no = (int)*a.n_occ, ne = (int)*a.n_emp;
+    for (int c0 = warp * 32; c0 < no; c0 += nwarps * 32) {
+        const bool active = c0 + lane < no;
+        const int s = a.list_occ[active ? c0 + lane : c0];
+        const int p = s / LL, j = (s / L) % L, k = s % L;
+        const double sum = occ_chunk(a.g, a.P, &nbt, a.g.i_off + p, j, k, s, active);
+        if (active) a.site_rate[s] = sum;
+    }
+    for (int c0 = warp * 32; c0 < ne; c0 += nwarps * 32) {
+        const bool active = c0 + lane < ne;
+        const int s = a.list_emp[active ? c0 + lane : c0];
+        const int p = s / LL, j = (s / L) % L, k = s % L;
+        const int i = a.g.i_off + p;
+        bool has_dep;
+        double dep;
+        const double sum = emp_chunk(a.g, a.P, &nbt, i, j, k, s, active, &has_dep, &dep);
+        if (active) {
+            a.site_rate[s] = sum;
+            if (i == a.g.n0 - 1) a.dep_rate[j * L + k] = has_dep ? dep : NAN;
+        }
     }
 }
 
@@ -100,27 +196,60 @@ __global__ void total_kernel(const double *seg, const int32_t *row_depcnt, doubl
     if (threadIdx.x == 0) { total[0] = t; ((long long *)total)[1] = nd; }
 }
 
-int rates_build(cet_ctx *c)
+// Dense evaluation of local planes [p_lo, p_hi): site_rate, dep_rate and the row sums.
+int rates_rows(cet_ctx *c, int p_lo, int p_hi)
 {
     CET_REQUIRE(c->cubic, "rates: context was created with cet_create_shape (thermal only)");
     CET_REQUIRE(c->have_rp, "rates: cet_set_rate_params has not been called");
+    if (p_hi <= p_lo) return 0;
     RatesArgs a;
     a.g = c->lat();
     a.P = c->rp;
     a.site_rate = c->site_rate; a.dep_rate = c->dep_rate;
     a.row_occ = c->row_occ; a.row_emp = c->row_emp; a.row_dep = c->row_dep; a.row_depcnt = c->row_depcnt;
-    a.p_lo = c->halo; a.p_hi = (int)(c->np - c->halo);
+    a.p_lo = p_lo; a.p_hi = p_hi; a.stamp = nullptr; a.stamp_id = 0;
     const int nrows = (a.p_hi - a.p_lo) * (int)c->n1;
     CET_REQUIRE(c->n1 <= 65535, "rates: L must fit 16-bit row indices");
+    CET_REQUIRE(c->nloc < (1ll << 31), "rates: the local lattice must have fewer than 2^31 sites");
     const size_t smem = RB_WARPS * dense_smem_per_warp((int)c->n1, true);
     CET_REQUIRE(smem <= 220 * 1024, "rates: L=%lld needs %zu B of shared memory per CTA", (long long)c->n1, smem);
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)
         CET_CUDA(cudaFuncSetAttribute(rates_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         ProfScope ps(c, PROF_RATES);
         rates_rows_kernel<<<(nrows + RB_WARPS - 1) / RB_WARPS, RB_WARPS * 32, smem, c->stream>>>(a);
     }
     CET_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Re-evaluate, on local planes [p_lo, p_hi), the sites whose stamp equals stamp_id.
+// lists: 2 * nloc int32 (occupied list, then empty list); counters: two device unsigned ints (zeroed by the caller).
+int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint32_t *stamp, uint32_t stamp_id, int32_t *lists,
+                     unsigned int *counters)
+{
+    if (p_hi <= p_lo) return 0;
+    DirtyArgs a;
+    a.g = c->lat();
+    a.P = c->rp;
+    a.site_rate = c->site_rate; a.dep_rate = c->dep_rate;
+    a.stamp = stamp; a.stamp_id = stamp_id; a.p_lo = p_lo; a.p_hi = p_hi;
+    a.list_occ = lists; a.list_emp = lists + c->nloc;
+    a.n_occ = counters; a.n_emp = counters + 1;
+    const int nrows = (p_hi - p_lo) * (int)c->n1;
+    dirty_scan_kernel<<<(nrows + RB_WARPS - 1) / RB_WARPS, RB_WARPS * 32, 0, c->stream>>>(a);
+    CET_CUDA(cudaGetLastError());
+    dirty_eval_kernel<<<148 * 6, RB_WARPS * 32, 0, c->stream>>>(a);
+    CET_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int rates_build(cet_ctx *c)
+{
+    const int p_lo = c->halo, p_hi = (int)(c->np - c->halo);
+    if (int rc = rates_rows(c, p_lo, p_hi)) return rc;
+    RatesArgs a;
+    a.g = c->lat(); a.p_lo = p_lo; a.p_hi = p_hi;
     const int npl = a.p_hi - a.p_lo;
     seg_kernel<<<(npl + 3) / 4, 128, 0, c->stream>>>(c->row_occ, c->row_emp, c->row_dep, c->seg, (int)c->n1,
                                                      a.p_lo, a.p_hi, a.g.i_off, a.g.n0);
@@ -129,6 +258,7 @@ int rates_build(cet_ctx *c)
                                            c->i_end == c->n0 ? 1 : 0);
     CET_CUDA(cudaGetLastError());
     c->rates_valid = true;
+    if (c->halo == 0) c->sweep_rates_valid = true;
     return 0;
 }
 

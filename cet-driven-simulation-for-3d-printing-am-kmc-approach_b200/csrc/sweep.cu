@@ -1,32 +1,43 @@
 // sweep.cu — synchronous-sublattice KMC sweeps for large lattices (no reference counterpart:
 // the reference executes ONE event per O(L^3) rate rebuild, kmc_simulation.py:246-332).
 //
-// One sweep visits every site once:
-//   decide  (dense, HBM/FP64-bound): per site, the event rates of kmc_event_rates.py:43-160 are
-//           evaluated from the sweep-start lattice; the site fires with p = 1-exp(-R_site*tau)
-//           and picks one of its events with probability rate/R_site.  Draws come from a
-//           counter-based Philox4x32-10 keyed by (seed, sweep, GLOBAL site index), so a site's
-//           decision does not depend on which GPU evaluates it.  A fired event claims the
-//           sites it will write (itself; a diffusion event also its target).
-//   apply   (sparse): conflicts are resolved by sublattice order — the 5x5x5 checkerboard
-//           colour of the source site, rotated every sweep, is the claim priority.  Two sites
-//           of one colour differ by multiples of 5 per axis, while two events can only collide
-//           when their sources differ by a neighbour offset or a difference of two offsets
-//           (every coordinate <= 4), so a colour never conflicts with itself and the outcome
-//           is deterministic.  Winners are applied exactly as kmc_simulation.py:280-327.
+// The per-site rate sums stay resident in HBM (site_rate, dep_rate — the same arrays the exact
+// BKL path uses) and are kept current by neighbour-rate updates, so one sweep is
+//   stream  (dense, HBM-bound, 8 B/site): every site reads its rate sum R, draws one uniform and
+//           fires with p = 1-exp(-R*tau); fired sites go to a compact list; per-plane totals of R
+//           are accumulated in a fixed order for the next time increment.  Draws come from a
+//           counter-based Philox4x32-10 keyed by (seed, sweep, GLOBAL site), so a site's decision
+//           does not depend on which GPU evaluates it;
+//   pick    (sparse): a fired site re-enumerates its <= 15 events (site_events, the same code
+//           that produced R) and picks one with probability rate/R, then claims the sites the
+//           event writes (itself; a diffusion event also its target);
+//   apply   (sparse): conflicts are resolved by sublattice order — the 5x5x5 checkerboard colour
+//           of the source site, rotated every sweep, is the claim priority.  Two sites of one
+//           colour differ by multiples of 5 per axis, while two events can only collide when
+//           their sources differ by a neighbour offset or a difference of two offsets (every
+//           coordinate <= 4), so a colour never conflicts with itself and the outcome is
+//           deterministic.  Winners are applied exactly as kmc_simulation.py:280-327 and mark the
+//           sites whose rates they invalidate (the changed sites and their 14 neighbours);
+//   refresh : the dense row pass of rates.cu restricted to the marked sites (coalesced, same
+//           arithmetic, so the resident rates stay bit-identical to a full rebuild);
 //   tau     for the next sweep from the totals of this one:
 //           tau = min(events_per_sweep / R_total, -ln(1-p_max) / R_max).
-// Slabs: a context with halo H >= 6 re-evaluates decisions of ghost sites to depth 4 and
-// resolves claims to depth 2, which is everything that can write an owned site; one halo
-// exchange per sweep (comm.cu) is the only data-path communication.  Plane sums are combined
-// in a fixed order so the trajectory is independent of the number of slabs.
+// A thermal step (every thermal_every sweeps) changes every rate: it is followed by a dense
+// rebuild (rates_rows).
+// Slabs: a context with halo H >= 6 evaluates ghost sites to depth 4 and resolves claims to
+// depth 2, which is everything that can write an owned site; after the one halo exchange per
+// sweep (comm.cu) the rates of the evaluated ghost planes are rebuilt densely (4 planes per
+// side).  Plane sums are combined in a fixed order so the trajectory is independent of the
+// number of slabs.
 #include "ctx.cuh"
-#include "dense_pass.cuh"
 #include "reduce.cuh"
 
 namespace cet {
 
 int thermal_cet_step(cet_ctx *c, const cet_thermal_params *p, const int32_t *stop_flag);
+int rates_rows(cet_ctx *c, int p_lo, int p_hi);                                  // rates.cu
+int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint32_t *stamp, uint32_t stamp_id, int32_t *lists,
+                     unsigned int *counters);
 int comm_sweep_reduce(cet_ctx *c, double *plane_sum, int n, double *max_inout);   // comm.cu
 int comm_halo_exchange(cet_ctx *c, int fields);
 
@@ -43,7 +54,7 @@ __device__ __forceinline__ u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1
     }
     return c;
 }
-// two uniforms in [0,1) with 53 random bits each
+// two uniforms in [0,1) with 53 random bits each, keyed by the global site
 __device__ __forceinline__ void philox_u2(uint64_t seed, uint64_t site, uint32_t sweep, uint32_t stream,
                                           double *u0, double *u1)
 {
@@ -53,31 +64,13 @@ __device__ __forceinline__ void philox_u2(uint64_t seed, uint64_t site, uint32_t
     *u0 = (double)(a >> 11) * 1.1102230246251565e-16;
     *u1 = (double)(b >> 11) * 1.1102230246251565e-16;
 }
+enum { STREAM_FIRE = 0, STREAM_PICK = 1, STREAM_ANGLES = 2, STREAM_SPECIES = 3, STREAM_DEFECT = 4 };
 
 struct Record {          // one fired event
-    long long src;       // local linear index of the source site
-    int32_t info;        // type | (slot+1) << 4 | atom << 12
-    int32_t colour_rank;
+    int32_t src;         // local linear index of the source site
+    int32_t info;        // type | (slot+1) << 4 | atom << 12 | colour rank << 20   (-1: no event)
     double theta, phi;   // orientation the written site receives (att: neighbour's; dep/nuc: drawn)
 };
-
-struct SweepArgs {
-    Lat g;
-    const double *theta, *phi;
-    cet_rate_params P;
-    SweepState *ss;
-    Record *records;
-    unsigned int cap_records;
-    unsigned long long *claim;
-    double *blk_sum, *blk_max;
-    int p_lo, p_hi;          // local planes whose sites are evaluated
-    int np;
-    uint64_t seed;
-    uint32_t sweep;
-    int rows_per_blk, blks_per_plane;
-};
-
-constexpr int SW_WARPS = 8;
 
 __device__ __forceinline__ int colour_rank(int i, int j, int k, uint32_t sweep)
 {
@@ -89,103 +82,70 @@ __device__ __forceinline__ unsigned long long claim_key(int rank, long long gsit
     return ((unsigned long long)(125 - rank) << 48) | (unsigned long long)(gsite + 1);
 }
 
-// A site fired: pick one of its events with probability rate / R (list order: dep first, then the
-// site's own events), record it and claim the sites it writes.
-__device__ __noinline__ void fire_event(const SweepArgs &a, int i, int j, int k, int64_t s, long long gsite,
-                                        double R, double dep, bool has_dep, double u_pick)
-{
-    const cet_rate_params &P = a.P;
-    const int L = a.g.L;
-    const int64_t LL = (int64_t)L * L;
-    const double x = u_pick * R;
-    double cum = 0.0;
-    int ety = -1, eslot = -1, eatom = 0;
-    bool found = false;
-    if (has_dep) {
-        cum = dep; ety = CET_EV_DEP; eatom = P.states_w;
-        if (cum >= x) found = true;
-    }
-    if (!found)
-        site_events(a.g, P, i, j, k, [&](int ty, int slot, double rate, int atom) {
-            if (found) return;
-            cum += rate; ety = ty; eslot = slot; eatom = atom;
-            if (cum >= x) found = true;
-        });
-    if (ety < 0) return;
-    Record rec;
-    rec.src = s;
-    rec.theta = 0.0; rec.phi = 0.0;
-    int64_t tgt = -1;
-    if (ety == CET_EV_DEP || ety == CET_EV_NUC) {
-        double ut, up;
-        philox_u2(a.seed, (uint64_t)gsite, a.sweep, 1u, &ut, &up);
-        rec.theta = __dmul_rn(3.141592653589793, ut);          // np.random.uniform(0, pi)
-        rec.phi = __dmul_rn(2 * 3.141592653589793, up);        // np.random.uniform(0, 2pi)
-        if (ety == CET_EV_DEP) {                               // kmc_event_rates.py:65-71
-            double us, unused;
-            philox_u2(a.seed, (uint64_t)gsite, a.sweep, 2u, &us, &unused);
-            eatom = dep_species(P, us);
-        }
-    } else {
-        tgt = s + CET_NB_DI(eslot) * LL + CET_NB_DJ(eslot) * L + CET_NB_DK(eslot);
-        if (ety == CET_EV_ATT) { rec.theta = a.theta[tgt]; rec.phi = a.phi[tgt]; }
-        else { rec.theta = a.theta[s]; rec.phi = a.phi[s]; }
-    }
-    const int rank = colour_rank(i, j, k, a.sweep);
-    rec.info = ety | ((eslot + 1) << 4) | (eatom << 12);
-    rec.colour_rank = rank;
-    const unsigned int slot = atomicAdd(&a.ss->n_records, 1u);
-    if (slot >= a.cap_records) { a.ss->overflow = 1; return; }
-    const unsigned long long key = claim_key(rank, gsite);
-    atomicMax(&a.claim[s], key);
-    if (ety == CET_EV_DIFF) atomicMax(&a.claim[tgt], key);
-    a.records[slot] = rec;
-}
+// ---- stream: one uniform per site against the resident rate sum --------------------------------
+constexpr int ST_THREADS = 256, ST_PER_THREAD = 4, ST_TILE = ST_THREADS * ST_PER_THREAD;
 
-// __grid_constant__: the argument block stays in constant memory even though fire_event takes
-// its address (no per-thread stack copy).
-__global__ void __launch_bounds__(SW_WARPS * 32) sweep_decide_kernel(const __grid_constant__ SweepArgs a)
+struct StreamArgs {
+    const double *site_rate, *dep_rate;   // dep_rate: plane of the global top (NaN = no event)
+    SweepState *ss;
+    int32_t *fired;
+    unsigned int cap_fired;
+    double *blk_sum, *blk_max;
+    int p_lo;                // first evaluated local plane
+    int top_plane;           // local index of the global top plane, or -1
+    int plane_sites;         // L*L
+    int tiles_per_plane;
+    int i_off;
+    uint64_t seed;
+    uint32_t sweep;
+};
+
+__global__ void __launch_bounds__(ST_THREADS) sweep_stream_kernel(const __grid_constant__ StreamArgs a)
 {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    __shared__ double s_sum[SW_WARPS], s_max[SW_WARPS];
-    const int L = a.g.L;
-    const int64_t LL = (int64_t)L * L;
+    __shared__ double s_sum[ST_THREADS / 32], s_max[ST_THREADS / 32];
+    __shared__ int s_list[ST_TILE];                 // fired sites of this tile (appended with one global atomic)
+    __shared__ unsigned int s_cnt, s_base;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int pl = blockIdx.x / a.tiles_per_plane, tile = blockIdx.x % a.tiles_per_plane;
+    const int p = a.p_lo + pl;
+    const int q0 = tile * ST_TILE + threadIdx.x * ST_PER_THREAD;      // first site of this thread in the plane
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int pl = blockIdx.x / a.blks_per_plane, jb = blockIdx.x % a.blks_per_plane;
-    const int p = a.p_lo + pl, j = jb * SW_WARPS + w;
-    const int i = a.g.i_off + p;
-    const bool stop = a.ss->terminated != 0;
-    const double tau = a.ss->tau;
-    double rsum = 0.0, rmax = 0.0;
-    if (j < L && !stop) {
-        const int64_t rbase = ((int64_t)p * L + j) * L;
-        RowLists lists;
-        lists.occ = (uint16_t *)(dyn_smem + (size_t)w * 2 * L * sizeof(uint16_t));
-        lists.emp = lists.occ + L;
-        row_classify(a.g, a.P, rbase, lists, nullptr);
-        // one site: accumulate the totals, draw, and (rarely) fire
-        auto visit = [&](int k, double R, bool has_dep, double dep, bool active) {
-            bool fire = false;
-            double u_pick = 0.0;
-            const long long gsite = (long long)i * LL + (long long)j * L + k;
-            if (active) {
-                rsum += R;
-                rmax = fmax(rmax, R);
-                if (R > 0.0 && tau > 0.0) {
-                    double u_fire;
-                    philox_u2(a.seed, (uint64_t)gsite, a.sweep, 0u, &u_fire, &u_pick);
-                    const double x = R * tau;                 // 1 - exp(-x) <= x: most sites reject here
-                    if (u_fire < x) fire = u_fire < -expm1(-x);
-                }
+    const double tau = a.ss->terminated ? 0.0 : a.ss->tau;
+    double R[ST_PER_THREAD];
+    const int64_t base = (int64_t)p * a.plane_sites;
+    const bool vec = (a.plane_sites % ST_PER_THREAD) == 0;           // every plane then starts 32-byte aligned
+    if (vec && q0 + ST_PER_THREAD <= a.plane_sites) {
+        const double2 *src = reinterpret_cast<const double2 *>(a.site_rate + base + q0);
+        const double2 v0 = src[0], v1 = src[1];
+        R[0] = v0.x; R[1] = v0.y; R[2] = v1.x; R[3] = v1.y;
+    } else {
+#pragma unroll
+        for (int e = 0; e < ST_PER_THREAD; ++e) R[e] = q0 + e < a.plane_sites ? a.site_rate[base + q0 + e] : 0.0;
+    }
+    if (p == a.top_plane) {
+#pragma unroll
+        for (int e = 0; e < ST_PER_THREAD; ++e)
+            if (q0 + e < a.plane_sites) {
+                const double d = a.dep_rate[q0 + e];
+                if (d == d) R[e] = d + R[e];
             }
-            if (fire) fire_event(a, i, j, k, rbase + k, gsite, R, dep, has_dep, u_pick);
-            __syncwarp();      // re-converge before the next chunk (keeps the dense part 32-wide)
-        };
-        row_occupied(a.g, a.P, i, j, rbase, lists,
-                     [&](int k, double sum, bool active) { visit(k, sum, false, 0.0, active); });
-        row_empty(a.g, a.P, i, j, rbase, lists, [&](int k, double sum, bool has_dep, double dep, bool active) {
-            visit(k, has_dep ? dep + sum : sum, has_dep, dep, active);
-        });
+    }
+    double rsum = 0.0, rmax = 0.0;
+#pragma unroll
+    for (int e = 0; e < ST_PER_THREAD; ++e) { rsum += R[e]; rmax = fmax(rmax, R[e]); }
+    if (tau > 0.0 && rmax > 0.0) {
+        // one Philox block serves the four sites of this thread: 32 random bits per fire test
+        const u32x4 r = philox4x32_10(u32x4{(uint32_t)(q0 >> 2), (uint32_t)(a.i_off + p), a.sweep, (uint32_t)STREAM_FIRE},
+                                      (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int e = 0; e < ST_PER_THREAD; ++e) {
+            const double u = ((double)bits[e] + 0.5) * 2.3283064365386963e-10;      // (0,1), 32 bits
+            const double x = R[e] * tau;
+            if (u < x && u < -expm1(-x))                      // 1 - exp(-x) <= x: most sites stop at the first test
+                s_list[atomicAdd(&s_cnt, 1u)] = (int32_t)(base + q0 + e);
+        }
     }
     rsum = warp_sum(rsum);
     rmax = warp_max(rmax);
@@ -193,13 +153,98 @@ __global__ void __launch_bounds__(SW_WARPS * 32) sweep_decide_kernel(const __gri
     __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0.0, m = 0.0;
-        for (int q = 0; q < SW_WARPS; ++q) { t += s_sum[q]; m = fmax(m, s_max[q]); }
+        for (int q = 0; q < ST_THREADS / 32; ++q) { t += s_sum[q]; m = fmax(m, s_max[q]); }
         a.blk_sum[blockIdx.x] = t;
         a.blk_max[blockIdx.x] = m;
+        s_base = s_cnt ? atomicAdd(&a.ss->n_fired, s_cnt) : 0u;
+    }
+    __syncthreads();
+    for (unsigned int q = threadIdx.x; q < s_cnt; q += ST_THREADS) {
+        if (s_base + q < a.cap_fired) a.fired[s_base + q] = s_list[q];
+        else a.ss->overflow = 1;
     }
 }
 
-// One warp per evaluated plane: fixed-order sum of the plane's block partials.  plane_sum is
+// ---- pick: choose the event of every fired site, record it and claim its write set --------------
+struct PickArgs {
+    Lat g;
+    const double *theta, *phi, *site_rate, *dep_rate;
+    cet_rate_params P;
+    SweepState *ss;
+    const int32_t *fired;
+    unsigned int cap_fired;
+    Record *records;
+    unsigned long long *claim;
+    uint64_t seed;
+    uint32_t sweep;
+};
+
+__global__ void __launch_bounds__(128) sweep_pick_kernel(const __grid_constant__ PickArgs a)
+{
+    const unsigned int n = min(a.ss->n_fired, a.cap_fired);
+    const int L = a.g.L;
+    const int64_t LL = (int64_t)L * L;
+    for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int s = a.fired[q];
+        const int p = (int)(s / LL), j = (int)((s / L) % L), k = s % L;
+        const int i = a.g.i_off + p;
+        const long long gsite = (long long)i * LL + (long long)j * L + k;
+        double R = a.site_rate[s], dep = 0.0;
+        bool has_dep = false;
+        if (i == a.g.n0 - 1) {
+            dep = a.dep_rate[(int64_t)j * L + k];
+            has_dep = dep == dep;
+            if (has_dep) R = dep + R;
+        }
+        double u_pick, unused;
+        philox_u2(a.seed, (uint64_t)gsite, a.sweep, STREAM_PICK, &u_pick, &unused);
+        // pick one event with probability rate / R (list order: dep, then the site's events)
+        const double x = u_pick * R;
+        double cum = 0.0;
+        int ety = -1, eslot = -1, eatom = 0;
+        bool found = false;
+        if (has_dep) {
+            cum = dep; ety = CET_EV_DEP; eatom = a.P.states_w;
+            if (cum >= x) found = true;
+        }
+        if (!found)
+            site_events(a.g, a.P, i, j, k, [&](int ty, int slot, double rate, int atom) {
+                if (found) return;
+                cum += rate; ety = ty; eslot = slot; eatom = atom;
+                if (cum >= x) found = true;
+            });
+        Record rec;
+        rec.src = s;
+        rec.theta = 0.0; rec.phi = 0.0;
+        rec.info = -1;
+        if (ety >= 0) {
+            int64_t tgt = -1;
+            if (ety == CET_EV_DEP || ety == CET_EV_NUC) {
+                double ut, up;
+                philox_u2(a.seed, (uint64_t)gsite, a.sweep, STREAM_ANGLES, &ut, &up);
+                rec.theta = __dmul_rn(3.141592653589793, ut);          // np.random.uniform(0, pi)
+                rec.phi = __dmul_rn(2 * 3.141592653589793, up);        // np.random.uniform(0, 2pi)
+                if (ety == CET_EV_DEP) {                               // kmc_event_rates.py:65-71
+                    double us;
+                    philox_u2(a.seed, (uint64_t)gsite, a.sweep, STREAM_SPECIES, &us, &unused);
+                    eatom = dep_species(a.P, us);
+                }
+            } else {
+                tgt = a.g.nb(s, eslot);
+                if (ety == CET_EV_ATT) { rec.theta = a.theta[tgt]; rec.phi = a.phi[tgt]; }
+                else { rec.theta = a.theta[s]; rec.phi = a.phi[s]; }
+            }
+            const int rank = colour_rank(i, j, k, a.sweep);
+            rec.info = ety | ((eslot + 1) << 4) | (eatom << 12) | (rank << 20);
+            const unsigned long long key = claim_key(rank, gsite);
+            atomicMax(&a.claim[s], key);
+            if (ety == CET_EV_DIFF) atomicMax(&a.claim[tgt], key);
+        }
+        a.records[q] = rec;
+    }
+}
+
+// One warp per evaluated plane: fixed-order sum of the plane's tile partials.  plane_sum is
 // indexed by GLOBAL plane so that every slab count produces the same numbers.
 __global__ void sweep_plane_reduce_kernel(const double *blk_sum, const double *blk_max, int blks_per_plane,
                                           int n_planes, int first_global, int own_lo, int own_hi,
@@ -231,6 +276,7 @@ __global__ void sweep_finalize_kernel(SweepState *ss, const double *plane_sum, i
     if (threadIdx.x == 0 && !ss->terminated) {
         const double rmax = *max_in;
         ss->time += ss->tau;                       // the sweep that just ran advanced time by its tau
+        ss->n_refreshed_total += (unsigned long long)ss->n_dirty + ss->n_dirty_emp;
         ss->sum_rate = total; ss->max_rate = rmax;
         if (total < 1e-25 || !finite_f64(total)) { // kmc_simulation.py:260-262
             ss->terminated = 1; ss->tau = 0.0;
@@ -243,39 +289,59 @@ __global__ void sweep_finalize_kernel(SweepState *ss, const double *plane_sum, i
     }
 }
 
+// ---- apply ---------------------------------------------------------------------------------------
 struct ApplyArgs {
     uint8_t *vox;
     double *theta, *phi, *vx, *vy, *vz;
     SweepState *ss;
     const Record *records;
-    unsigned int cap_records;
+    unsigned int cap_fired;
     unsigned long long *claim;
+    uint32_t *stamp;
     cet_rate_params P;
-    int L, i_off;
+    int L, n0, i_off, np;
     int c_lo, c_hi;        // local planes with complete claims
     int own_lo, own_hi;    // local planes owned by this slab (for the counters)
     uint64_t seed;
-    uint32_t sweep;
+    uint32_t sweep, stamp_id;
     double defect_fraction;
 };
 
-__global__ void sweep_apply_kernel(const ApplyArgs a)
+// request a rate refresh of the site and of its neighbours: the refresh pass (rates_rows_dirty)
+// re-evaluates every site whose stamp carries this sweep's id
+__device__ __forceinline__ void mark_neighbourhood(const ApplyArgs &a, int site)
 {
-    const unsigned int n = min(a.ss->n_records, a.cap_records);
-    const int64_t LL = (int64_t)a.L * a.L;
-    unsigned long long fired = 0, applied = 0, nuc = 0;
+    const int LL = a.L * a.L;
+    const int p = site / LL, j = (site / a.L) % a.L, k = site % a.L;
+    a.stamp[site] = a.stamp_id;
+    const unsigned inb = inbounds_mask(a.i_off + p, j, k, a.n0, a.L);    // inside the GLOBAL lattice ...
+#pragma unroll 1
+    for (int o = 0; o < 14; ++o) {
+        if (!(inb >> o & 1u)) continue;
+        const int pn = p + c_nb_off[o][0];
+        if (pn < 0 || pn >= a.np) continue;                             // ... and inside the local planes
+        a.stamp[site + (c_nb_off[o][0] * a.L + c_nb_off[o][1]) * a.L + c_nb_off[o][2]] = a.stamp_id;
+    }
+}
+
+__global__ void __launch_bounds__(128) sweep_apply_kernel(const __grid_constant__ ApplyArgs a)
+{
+    const unsigned int n = min(a.ss->n_fired, a.cap_fired);
+    const int LL = a.L * a.L;
+    int fired = 0, applied = 0, nuc = 0;
     for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         const Record rec = a.records[q];
-        const int ety = rec.info & 15, eslot = ((rec.info >> 4) & 255) - 1, eatom = rec.info >> 12;
-        const int64_t s = rec.src;
-        const int p = (int)(s / LL), j = (int)((s / a.L) % a.L), k = (int)(s % a.L);
+        if (rec.info < 0) continue;
+        const int ety = rec.info & 15, eslot = ((rec.info >> 4) & 255) - 1, eatom = (rec.info >> 12) & 255;
+        const int rank = rec.info >> 20;
+        const int s = rec.src;
+        const int p = s / LL, j = (s / a.L) % a.L, k = s % a.L;
         const long long gsite = (long long)(a.i_off + p) * LL + (long long)j * a.L + k;
-        const unsigned long long key = claim_key(rec.colour_rank, gsite);
-        int64_t tgt = -1;
-        int pt = p;
+        const unsigned long long key = claim_key(rank, gsite);
+        int tgt = -1, pt = p;
         if (ety == CET_EV_DIFF || ety == CET_EV_ATT) {
-            tgt = s + CET_NB_DI(eslot) * LL + CET_NB_DJ(eslot) * a.L + CET_NB_DK(eslot);
-            if (ety == CET_EV_DIFF) pt = p + CET_NB_DI(eslot);
+            tgt = s + (c_nb_off[eslot][0] * a.L + c_nb_off[eslot][1]) * a.L + c_nb_off[eslot][2];
+            if (ety == CET_EV_DIFF) pt = p + c_nb_off[eslot][0];
         }
         const bool owned = p >= a.own_lo && p < a.own_hi;
         if (owned) ++fired;
@@ -284,7 +350,7 @@ __global__ void sweep_apply_kernel(const ApplyArgs a)
         const unsigned long long ct = (ety == CET_EV_DIFF) ? a.claim[tgt] : key;
         const bool win = complete && cs == key && ct == key;
         if (win) {
-            int64_t upd = s;
+            int upd = s;
             double ux, uy, uz;
             unit_vector(rec.theta, rec.phi, &ux, &uy, &uz);          // same bits as the source's resident vector
             if (ety == CET_EV_DIFF) {                                    // kmc_simulation.py:292-303
@@ -303,7 +369,7 @@ __global__ void sweep_apply_kernel(const ApplyArgs a)
             }
             if (a.defect_fraction > 0.0) {                               // :323-327
                 double u2, unused;
-                philox_u2(a.seed, (uint64_t)gsite, a.sweep, 3u, &u2, &unused);
+                philox_u2(a.seed, (uint64_t)gsite, a.sweep, STREAM_DEFECT, &u2, &unused);
                 if (u2 < a.defect_fraction) {
                     a.vox[upd] = (uint8_t)((a.vox[upd] & 0xF0) | a.P.defect_id);
                     a.theta[upd] = 0.0; a.phi[upd] = 0.0;
@@ -311,22 +377,24 @@ __global__ void sweep_apply_kernel(const ApplyArgs a)
                 }
             }
             if (owned) ++applied;
+            mark_neighbourhood(a, s);
+            if (ety == CET_EV_DIFF) mark_neighbourhood(a, tgt);
         }
         // release the claims this event holds (only the top claimant of a site clears it)
         if (cs == key) a.claim[s] = 0ull;
         if (ety == CET_EV_DIFF && ct == key) a.claim[tgt] = 0ull;
     }
-    fired = warp_sum_i((int)fired); applied = warp_sum_i((int)applied); nuc = warp_sum_i((int)nuc);
+    fired = warp_sum_i(fired); applied = warp_sum_i(applied); nuc = warp_sum_i(nuc);
     if ((threadIdx.x & 31) == 0) {
-        if (fired) atomicAdd(&a.ss->n_fired, fired);
-        if (applied) atomicAdd(&a.ss->n_applied, applied);
-        if (nuc) atomicAdd(&a.ss->n_nuc, nuc);
+        if (fired) atomicAdd(&a.ss->n_fired_total, (unsigned long long)fired);
+        if (applied) atomicAdd(&a.ss->n_applied, (unsigned long long)applied);
+        if (nuc) atomicAdd(&a.ss->n_nuc, (unsigned long long)nuc);
     }
 }
 
 __global__ void sweep_reset_kernel(SweepState *ss, double *max_slot)
 {
-    ss->n_records = 0;
+    ss->n_fired = 0; ss->n_dirty = 0; ss->n_dirty_emp = 0;
     *max_slot = 0.0;
 }
 
@@ -340,15 +408,23 @@ static int sweep_alloc(cet_ctx *c)
         CET_CUDA(cudaMalloc(&c->claim, (size_t)c->nloc * sizeof(unsigned long long)));
         CET_CUDA(cudaMemsetAsync(c->claim, 0, (size_t)c->nloc * sizeof(unsigned long long), c->stream));
     }
-    if (!c->records) {
-        size_t cap = (size_t)c->nloc / 4 + 4096;
-        if (cap > 0x7fffffffull) cap = 0x7fffffffull;
-        CET_CUDA(cudaMalloc(&c->records, cap * sizeof(Record)));
-        c->cap_records = cap;
+    if (!c->stamp) {
+        CET_CUDA(cudaMalloc(&c->stamp, (size_t)c->nloc * sizeof(uint32_t)));
+        CET_CUDA(cudaMemsetAsync(c->stamp, 0, (size_t)c->nloc * sizeof(uint32_t), c->stream));
     }
-    const int bpp = (int)((c->n1 + SW_WARPS - 1) / SW_WARPS);
+    if (!c->dirty) {
+        c->cap_dirty = (size_t)c->nloc;               // occupied list + empty list, one entry per site each
+        CET_CUDA(cudaMalloc(&c->dirty, 2 * c->cap_dirty * sizeof(int32_t)));
+    }
+    if (!c->fired) {
+        c->cap_fired = (size_t)c->nloc / 8 + 4096;
+        CET_CUDA(cudaMalloc(&c->fired, c->cap_fired * sizeof(int32_t)));
+        CET_CUDA(cudaMalloc(&c->records, c->cap_fired * sizeof(Record)));
+        c->cap_records = c->cap_fired;
+    }
+    const int tpp = (int)((c->plane + ST_TILE - 1) / ST_TILE);
     if (!c->blk_sum) {
-        c->n_blk = (int64_t)bpp * c->np;
+        c->n_blk = (int64_t)tpp * c->np;
         CET_CUDA(cudaMalloc(&c->blk_sum, (size_t)c->n_blk * sizeof(double)));
         CET_CUDA(cudaMalloc(&c->blk_max, (size_t)c->n_blk * sizeof(double)));
         CET_CUDA(cudaMalloc(&c->plane_sum, (size_t)(c->n0 + 2) * sizeof(double)));
@@ -395,18 +471,15 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
     CET_REQUIRE(c->world == 1 || c->halo >= 6, "cet_sweep_run: slabs need halo >= 6");
     CET_REQUIRE(c->world > 1 || (c->i_begin == 0 && c->i_end == c->n0),
                 "cet_sweep_run: a partial slab needs cet_comm_init");
+    CET_REQUIRE(c->nloc < (1ll << 31), "cet_sweep_run: the local lattice must have fewer than 2^31 sites");
     cet::DeviceGuard dg(c->device);
     if (int rc = sweep_alloc(c)) return rc;
     const SlabRanges R = slab_ranges(c);
-    const int bpp = (int)((c->n1 + SW_WARPS - 1) / SW_WARPS);
+    const int tpp = (int)((c->plane + ST_TILE - 1) / ST_TILE);
     const int n_eval = R.eval_hi - R.eval_lo;
     const int i_off = (int)(c->i_begin - c->halo);
+    const int top_plane = (int)(c->n0 - 1 - i_off);
     double *max_slot = c->plane_sum + c->n0;      // plane_sum[n0] holds the running max
-    CET_REQUIRE(c->n1 <= 65535, "cet_sweep_run: L must fit 16-bit row indices");
-    const size_t decide_smem = (size_t)SW_WARPS * 2 * c->n1 * sizeof(uint16_t);
-    if (decide_smem > 48 * 1024)
-        CET_CUDA(cudaFuncSetAttribute(sweep_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)decide_smem));
 
     SweepState before;
     CET_CUDA(cudaMemcpyAsync(&before, c->sweep, sizeof(before), cudaMemcpyDeviceToHost, c->stream));
@@ -418,58 +491,91 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
             if (int rc = thermal_cet_step(c, tp, &c->sweep->terminated)) return rc;
             if (c->world > 1) if (int rc = comm_halo_exchange(c, 4)) return rc;
         }
+        if (!c->sweep_rates_valid) {                 // new lattice, new T or new parameters: dense rebuild
+            if (int rc = rates_rows(c, R.eval_lo, R.eval_hi)) return rc;
+            c->sweep_rates_valid = true;
+        }
         sweep_reset_kernel<<<1, 1, 0, c->stream>>>(c->sweep, max_slot);
         CET_CUDA(cudaMemsetAsync(c->plane_sum, 0, (size_t)c->n0 * sizeof(double), c->stream));
-        SweepArgs a;
-        a.g = c->lat(); a.theta = c->theta; a.phi = c->phi; a.P = c->rp; a.ss = c->sweep;
-        a.records = (Record *)c->records; a.cap_records = (unsigned int)c->cap_records;
-        a.claim = c->claim; a.blk_sum = c->blk_sum; a.blk_max = c->blk_max;
-        a.p_lo = R.eval_lo; a.p_hi = R.eval_hi; a.np = (int)c->np;
-        a.seed = sp->seed; a.sweep = (uint32_t)c->sweep_index;
-        a.rows_per_blk = SW_WARPS; a.blks_per_plane = bpp;
         {
+            StreamArgs a;
+            a.site_rate = c->site_rate; a.dep_rate = c->dep_rate; a.ss = c->sweep;
+            a.fired = c->fired; a.cap_fired = (unsigned int)c->cap_fired;
+            a.blk_sum = c->blk_sum; a.blk_max = c->blk_max;
+            a.p_lo = R.eval_lo;
+            a.top_plane = (top_plane >= R.eval_lo && top_plane < R.eval_hi) ? top_plane : -1;
+            a.plane_sites = (int)c->plane; a.tiles_per_plane = tpp; a.i_off = i_off;
+            a.seed = sp->seed; a.sweep = (uint32_t)c->sweep_index;
             ProfScope ps(c, PROF_DECIDE);
-            sweep_decide_kernel<<<n_eval * bpp, SW_WARPS * 32, decide_smem, c->stream>>>(a);
+            sweep_stream_kernel<<<n_eval * tpp, ST_THREADS, 0, c->stream>>>(a);
         }
         CET_CUDA(cudaGetLastError());
         sweep_plane_reduce_kernel<<<(n_eval + 3) / 4, 128, 0, c->stream>>>(
-            c->blk_sum, c->blk_max, bpp, n_eval, i_off + R.eval_lo, (int)c->i_begin, (int)c->i_end,
+            c->blk_sum, c->blk_max, tpp, n_eval, i_off + R.eval_lo, (int)c->i_begin, (int)c->i_end,
             c->plane_sum, max_slot);
         CET_CUDA(cudaGetLastError());
         if (c->world > 1) if (int rc = comm_sweep_reduce(c, c->plane_sum, (int)c->n0, max_slot)) return rc;
-        ApplyArgs b;
-        b.vox = c->vox; b.theta = c->theta; b.phi = c->phi; b.vx = c->vx; b.vy = c->vy; b.vz = c->vz;
-        b.ss = c->sweep;
-        b.records = (const Record *)c->records; b.cap_records = (unsigned int)c->cap_records;
-        b.claim = c->claim; b.P = c->rp; b.L = (int)c->n1; b.i_off = i_off;
-        b.c_lo = R.claim_lo; b.c_hi = R.claim_hi; b.own_lo = R.own_lo; b.own_hi = R.own_hi;
-        b.seed = sp->seed; b.sweep = (uint32_t)c->sweep_index; b.defect_fraction = sp->defect_fraction;
         {
-            ProfScope ps(c, PROF_APPLY);
-            sweep_apply_kernel<<<148 * 4, 256, 0, c->stream>>>(b);
+            PickArgs a;
+            a.g = c->lat(); a.theta = c->theta; a.phi = c->phi; a.site_rate = c->site_rate; a.dep_rate = c->dep_rate;
+            a.P = c->rp; a.ss = c->sweep; a.fired = c->fired; a.cap_fired = (unsigned int)c->cap_fired;
+            a.records = (Record *)c->records; a.claim = c->claim;
+            a.seed = sp->seed; a.sweep = (uint32_t)c->sweep_index;
+            ProfScope ps(c, PROF_PICK);
+            sweep_pick_kernel<<<148 * 8, 128, 0, c->stream>>>(a);
         }
         CET_CUDA(cudaGetLastError());
+        {
+            ApplyArgs b;
+            b.vox = c->vox; b.theta = c->theta; b.phi = c->phi; b.vx = c->vx; b.vy = c->vy; b.vz = c->vz;
+            b.ss = c->sweep; b.records = (const Record *)c->records; b.cap_fired = (unsigned int)c->cap_fired;
+            b.claim = c->claim; b.stamp = c->stamp;
+            b.P = c->rp; b.L = (int)c->n1; b.n0 = (int)c->n0; b.i_off = i_off; b.np = (int)c->np;
+            b.c_lo = R.claim_lo; b.c_hi = R.claim_hi; b.own_lo = R.own_lo; b.own_hi = R.own_hi;
+            b.seed = sp->seed; b.sweep = (uint32_t)c->sweep_index;
+            b.stamp_id = (uint32_t)(c->sweep_index + 1);      // stamps start at 0
+            b.defect_fraction = sp->defect_fraction;
+            ProfScope ps(c, PROF_APPLY);
+            sweep_apply_kernel<<<148 * 8, 128, 0, c->stream>>>(b);
+        }
+        CET_CUDA(cudaGetLastError());
+        {
+            ProfScope ps(c, PROF_REFRESH);
+            if (int rc = rates_rows_dirty(c, R.eval_lo, R.eval_hi, c->stamp, (uint32_t)(c->sweep_index + 1), c->dirty,
+                                          &c->sweep->n_dirty))
+                return rc;
+        }
         sweep_finalize_kernel<<<1, 256, 0, c->stream>>>(c->sweep, c->plane_sum, (int)c->n0, max_slot,
                                                         sp->events_per_sweep, sp->p_max);
         CET_CUDA(cudaGetLastError());
         if (c->world > 1) {
-            ProfScope ps(c, PROF_HALO);
-            if (int rc = comm_halo_exchange(c, 1 | 2)) return rc;
+            {
+                ProfScope ps(c, PROF_HALO);
+                if (int rc = comm_halo_exchange(c, 1 | 2)) return rc;
+            }
+            // the ghost planes now hold the owners' lattice: rebuild the rates evaluated there
+            if (int rc = rates_rows(c, R.eval_lo, R.own_lo)) return rc;
+            if (int rc = rates_rows(c, R.own_hi, R.eval_hi)) return rc;
         }
         c->sweep_index++;
     }
-    c->rates_valid = false;
+    c->rates_valid = false;          // the BKL sum hierarchy is not maintained by the sweeps
     SweepState after;
     CET_CUDA(cudaMemcpyAsync(&after, c->sweep, sizeof(after), cudaMemcpyDeviceToHost, c->stream));
     CET_CUDA(cudaStreamSynchronize(c->stream));
+    if (after.dirty_overflow) {      // refresh list overflowed: the resident rates are stale
+        c->sweep_rates_valid = false;
+        CET_CUDA(cudaMemsetAsync(&c->sweep->dirty_overflow, 0, sizeof(unsigned int), c->stream));
+    }
     res->sweeps_done = n_sweeps;
-    res->events_fired = (int64_t)(after.n_fired - before.n_fired);
+    res->events_fired = (int64_t)(after.n_fired_total - before.n_fired_total);
     res->events_applied = (int64_t)(after.n_applied - before.n_applied);
     res->nucleation_count = (int64_t)(after.n_nuc - before.n_nuc);
     res->sweep_index = c->sweep_index;
     res->time = after.time - before.time;
     res->last_total_rate = after.sum_rate; res->last_max_rate = after.max_rate; res->last_tau = after.tau;
+    res->sites_refreshed = (int64_t)(after.n_refreshed_total - before.n_refreshed_total);
     res->terminated = after.terminated;
-    res->overflow = (int32_t)after.overflow;
+    res->overflow = (int32_t)(after.overflow | (after.dirty_overflow << 1));
     return 0;
 }

@@ -152,7 +152,7 @@ static int launch_thermal(cet_ctx *c, ThermalArgs &a)
         CET_CUDA(cudaMemcpyAsync(c->T2 + (int64_t)a.p_hi * plane, c->T + (int64_t)a.p_hi * plane,
                                  (size_t)(c->np - a.p_hi) * plane * 8, cudaMemcpyDeviceToDevice, c->stream));
     double *t = c->T; c->T = c->T2; c->T2 = t;
-    c->rates_valid = false;
+    c->rates_valid = false; c->sweep_rates_valid = false;
     return 0;
 }
 
@@ -207,7 +207,7 @@ int cet_thermal_fill_gradient(cet_ctx *c, double t0, double g)
     fill_gradient_kernel<<<148 * 8, 256, 0, c->stream>>>(c->T, c->plane, (int)c->np,
                                                          (int)(c->i_begin - c->halo), (int)c->n0, t0, g);
     CET_CUDA(cudaGetLastError());
-    c->rates_valid = false;
+    c->rates_valid = false; c->sweep_rates_valid = false;
     return 0;
 }
 

@@ -89,6 +89,7 @@ typedef struct cet_sweep_result {
     double last_total_rate, last_max_rate, last_tau;
     int32_t terminated;
     int32_t overflow;          /* the fired-event list overflowed (events dropped): lower events_per_sweep */
+    int64_t sites_refreshed;   /* sites whose rates the neighbour-rate updates re-evaluated */
 } cet_sweep_result;
 
 /* ---- library ---- */
@@ -176,8 +177,9 @@ int cet_halo_exchange(cet_ctx *ctx, int fields);
 int cet_allreduce_f64(cet_ctx *ctx, double *inout_host, int n, int op /* 0 sum, 1 max */);
 
 /* ---- per-kernel device timing: CUDA event pairs recorded on the context stream around every
- * launch of a kind while enabled.  kind: 0 sweep decide, 1 sweep apply, 2 thermal stencil,
- * 3 dense rate kernel, 4 halo exchange, 5 whole sweep. */
+ * launch of a kind while enabled.  kind: 0 sweep stream (fire decision), 1 sweep apply,
+ * 2 thermal stencil, 3 dense rate kernel, 4 halo exchange, 5 whole sweep, 6 sweep pick,
+ * 7 neighbour-rate refresh. */
 int cet_profile_enable(cet_ctx *ctx, int on);
 int cet_profile_read(cet_ctx *ctx, int kind, double *ms_total, int64_t *launches, int reset);
 

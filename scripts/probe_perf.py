@@ -27,12 +27,17 @@ def main():
             print(f"  {name}: {ms:.3f} ms  {N/ms*1e3:.3e} sites/s  {N*bytes_per_site/ms/1e6:.0f} GB/s algorithmic", flush=True)
         ctx.upload(T=T)
         sp = cetkmc._lib.SweepParams()
-        sp.seed, sp.events_per_sweep, sp.p_max, sp.defect_fraction, sp.thermal_every = 1, 0.02 * N, 0.25, 0.0, 0
-        r = ctx.sweep_run(3, sp, None)
-        ctx.timer_begin()
-        r = ctx.sweep_run(10, sp, None)
-        ms = ctx.timer_end_ms() / 10
-        print(f"  sweep: {ms:.3f} ms  {N/ms*1e3:.3e} site-updates/s  applied/sweep={r['events_applied']/10:.0f} fired/sweep={r['events_fired']/10:.0f} tau={r['last_tau']:.3e}", flush=True)
+        for eps, pmax in ((0.02, 0.25), (0.005, 0.1), (0.001, 0.05)):
+            sp.seed, sp.events_per_sweep, sp.p_max, sp.defect_fraction, sp.thermal_every = 1, eps * N, pmax, 0.0, 0
+            r = ctx.sweep_run(3, sp, None)
+            ctx.profile_enable(True)
+            ctx.timer_begin()
+            r = ctx.sweep_run(10, sp, None)
+            ms = ctx.timer_end_ms() / 10
+            ctx.profile_enable(False)
+            kb = {k: ctx.profile_read(k)[0] / 10 for k in ("decide", "pick", "apply", "refresh", "rates")}
+            print(f"  sweep eps={eps} pmax={pmax}: {ms:.3f} ms  {N/ms*1e3:.3e} site-updates/s  applied/sweep={r['events_applied']/10:.0f} fired/sweep={r['events_fired']/10:.0f} ovf={r['overflow']} "
+                  + " ".join(f"{k}={v:.3f}" for k, v in kb.items()), flush=True)
         # fresh lattice (mostly empty): the HBM-bound regime
         st = np.zeros((L, L, L), np.uint8); st[:, :, 0] = (np.random.default_rng(0).random((L, L)) < 0.02)
         ctx.upload_packed(st); ctx.upload(theta=np.zeros((L, L, L)), phi=np.zeros((L, L, L)))

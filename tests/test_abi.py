@@ -38,7 +38,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(L.ThermalFullParams) == 56
     assert C.sizeof(L.KmcResult) == 72
     assert C.sizeof(L.SweepParams) == 40
-    assert C.sizeof(L.SweepResult) == 80
+    assert C.sizeof(L.SweepResult) == 88
 
 
 def test_no_cpu_fallback():
