@@ -257,7 +257,7 @@ int cet_upload(cet_ctx *c, const int64_t *state, const double *theta, const doub
     if ((theta || phi) && !c->cubic) { set_error("cet_upload: theta/phi need a cubic context"); return 1; }
     if (theta) CET_CUDA(cudaMemcpyAsync(c->theta + off, theta, fb, cudaMemcpyHostToDevice, c->stream));
     if (phi) CET_CUDA(cudaMemcpyAsync(c->phi + off, phi, fb, cudaMemcpyHostToDevice, c->stream));
-    if (T) CET_CUDA(cudaMemcpyAsync(c->T + off, T, fb, cudaMemcpyHostToDevice, c->stream));
+    if (T) { CET_CUDA(cudaMemcpyAsync(c->T + off, T, fb, cudaMemcpyHostToDevice, c->stream)); c->T_finite = false; }
     if (state || defects) {
         const size_t need = (size_t)n * sizeof(int64_t) * ((state ? 1 : 0) + (defects ? 1 : 0)) + 256;
         if (int rc = ensure_stage(c, need)) return rc;

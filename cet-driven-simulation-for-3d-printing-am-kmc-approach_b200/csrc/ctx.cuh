@@ -84,6 +84,7 @@ struct cet_ctx {
     int32_t *row_depcnt = nullptr;
     double *total = nullptr;          // [0] total, [1] (as int64) n_dep
     double *q_top = nullptr;
+    bool T_finite = false;            // T holds no NaN/inf (set by a nan_to_num stencil pass, cleared by uploads)
     bool rates_valid = false;         // site_rate / dep_rate and the BKL sum hierarchy valid on the owned planes
     bool sweep_rates_valid = false;   // site_rate / dep_rate valid on the planes the sweep evaluates
 

@@ -457,6 +457,7 @@ extern "C" int cet_sweep_reset(cet_ctx *c)
     cet::DeviceGuard dg(c->device);
     if (c->sweep) CET_CUDA(cudaMemsetAsync(c->sweep, 0, sizeof(SweepState), c->stream));
     c->sweep_index = 0;
+    c->T_finite = false;          // a terminated run skips its stencil passes: re-check T next time
     return 0;
 }
 

@@ -105,6 +105,112 @@ __global__ void __launch_bounds__(TH_TK *TH_TJ) thermal_kernel(ThermalArgs a)
     }
 }
 
+// Fast path (n2 a multiple of V = 2 or 4): V consecutive k per thread with 16-byte loads/stores,
+// the k-neighbours exchanged by warp shuffles, the i-neighbours kept in a register queue while
+// the CTA marches over TH2_PLANES planes; only the j-neighbour rows are re-read (from L1/L2: the
+// same CTA loaded them as centre rows one thread-row away).  Per V outputs: 3*V/2 vector loads,
+// V/2 vector stores, 2 shuffles.
+constexpr int TH2_TJ = 8, TH2_PLANES = 16;
+
+template <int V, bool NANFIX>
+struct RowVec {
+    double v[V];
+    __device__ __forceinline__ void load(const double *p, double nan_value)
+    {
+#pragma unroll
+        for (int e = 0; e < V; e += 2) {
+            const double2 t = *reinterpret_cast<const double2 *>(p + e);
+            v[e] = t.x; v[e + 1] = t.y;
+        }
+        if (NANFIX) {
+#pragma unroll
+            for (int e = 0; e < V; ++e)      // one compare in the common case: NaN and +-inf fail |v| <= DBL_MAX
+                if (!(fabs(v[e]) <= 1.7976931348623157e308)) v[e] = fix_nan(v[e], 1, nan_value);
+        }
+    }
+};
+
+template <bool FULL, bool NANFIX, int V>
+__global__ void __launch_bounds__(32 * TH2_TJ) thermal_kernel_v2(const ThermalArgs a)
+{
+    const int lane = threadIdx.x;
+    const int k0 = (blockIdx.x * 32 + lane) * V;
+    const int j = blockIdx.y * TH2_TJ + threadIdx.y;
+    const int p0 = a.p_lo + blockIdx.z * TH2_PLANES;
+    if (j >= a.n1) return;                                   // whole warp (threadIdx.y is per warp)
+    const bool in = k0 < a.n2;                               // n2 % V == 0: the whole vector is inside
+    const int64_t plane = (int64_t)a.n1 * a.n2;
+    const int jm = j > 0 ? j - 1 : 0, jp = j < a.n1 - 1 ? j + 1 : a.n1 - 1;
+    const int p1 = min(p0 + TH2_PLANES, a.p_hi);
+    const int kc = in ? k0 : 0;                              // inactive lanes read a valid address
+    const bool stop = a.stop != nullptr && *a.stop != 0;
+    // row pointers of plane p0, bumped by one plane per iteration
+    const double *pc = a.Tin + (int64_t)p0 * plane + (int64_t)j * a.n2 + kc;
+    const double *pm = a.Tin + (int64_t)p0 * plane + (int64_t)jm * a.n2 + kc;
+    const double *pp = a.Tin + (int64_t)p0 * plane + (int64_t)jp * a.n2 + kc;
+    double *po = a.Tout + (int64_t)p0 * plane + (int64_t)j * a.n2 + kc;
+    int gi = a.i_off + p0;
+    RowVec<V, NANFIX> below, centre, above, l1, r1;
+    below.load(gi > 0 ? pc - plane : pc, a.nan_value);
+    centre.load(pc, a.nan_value);
+    for (int p = p0; p < p1; ++p, ++gi) {
+        above.load(gi < a.n0 - 1 ? pc + plane : pc, a.nan_value);
+        l1.load(pm, a.nan_value);
+        r1.load(pp, a.nan_value);
+        // k neighbours: left of v[0] and right of v[V-1] come from the adjacent lanes
+        double left = __shfl_up_sync(0xffffffffu, centre.v[V - 1], 1);
+        double right = __shfl_down_sync(0xffffffffu, centre.v[0], 1);
+        if (lane == 0) {
+            left = centre.v[0];
+            if (k0 > 0) { left = pc[-1]; if (NANFIX) left = fix_nan(left, 1, a.nan_value); }
+        }
+        if (lane == 31 || k0 + V >= a.n2) {
+            right = centre.v[V - 1];
+            if (in && k0 + V < a.n2) { right = pc[V]; if (NANFIX) right = fix_nan(right, 1, a.nan_value); }
+        }
+        double out[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const double c = centre.v[e];
+            const double kl = e == 0 ? left : centre.v[e > 0 ? e - 1 : 0];
+            const double kr = e == V - 1 ? right : centre.v[e < V - 1 ? e + 1 : V - 1];
+            const double m2c = __dmul_rn(c, -2.0);
+            const double t0 = __dadd_rn(m2c, __dadd_rn(below.v[e], above.v[e]));
+            const double t1 = __dadd_rn(m2c, __dadd_rn(l1.v[e], r1.v[e]));
+            const double t2 = __dadd_rn(m2c, __dadd_rn(kl, kr));
+            double lap = __dadd_rn(__dadd_rn(t0, t1), t2);
+            lap = __dmul_rn(lap, a.inv_dx2);
+            double v;
+            if (!FULL) {
+                v = __dadd_rn(c, __dmul_rn(a.dt_alpha, lap));
+            } else {
+                const int64_t s = (int64_t)p * plane + (int64_t)j * a.n2 + kc + e;
+                const double q = (gi == a.n0 - 1) ? a.q_top[(int64_t)j * a.n2 + kc + e] : 0.0;
+                const bool solidified = (a.vox_prev[s] & 0x0F) == 0 && (a.vox[s] & 0x0F) != 0;
+                const double dFdt = solidified ? a.inv_dt_latent : 0.0;
+                const double dTdt = __dadd_rn(__dadd_rn(__dmul_rn(a.alpha, lap), __ddiv_rn(q, a.rho_cp)),
+                                              __dmul_rn(a.latent_over_cp, dFdt));
+                v = __dadd_rn(c, __dmul_rn(a.dt, dTdt));
+            }
+            if (v < a.lo) v = a.lo;       // np.clip: NaN stays NaN
+            if (v > a.hi) v = a.hi;
+            out[e] = v;
+        }
+        if (in) {
+#pragma unroll
+            for (int e = 0; e < V; e += 2) {
+                double2 o;
+                if (stop) o = *reinterpret_cast<const double2 *>(pc + e);
+                else { o.x = out[e]; o.y = out[e + 1]; }
+                *reinterpret_cast<double2 *>(po + e) = o;
+            }
+        }
+        below = centre;
+        centre = above;
+        pc += plane; pm += plane; pp += plane; po += plane;
+    }
+}
+
 __global__ void fill_gradient_kernel(double *T, int64_t plane, int np, int i_off, int n0, double t0, double g)
 {
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < plane * np;
@@ -135,10 +241,26 @@ static int launch_thermal(cet_ctx *c, ThermalArgs &a)
     a.np = (int)c->np;
     thermal_range(c, &a.p_lo, &a.p_hi);
     if (a.p_hi <= a.p_lo) return 0;
-    dim3 block(TH_TK, TH_TJ);
-    dim3 grid((unsigned)((c->n2 + TH_TK - 1) / TH_TK), (unsigned)((c->n1 + TH_TJ - 1) / TH_TJ),
-              (unsigned)((a.p_hi - a.p_lo + TH_PLANES - 1) / TH_PLANES));
-    {
+    // np.nan_to_num is the identity on a finite field, and a finite field stays finite under the
+    // clipped update: once a fixing pass has run (or the field is known finite) skip the checks.
+    const bool nanfix = a.nan_to_num && !c->T_finite;
+    if (c->n2 % 2 == 0) {
+        const int V = (c->n2 % 4 == 0) ? 4 : 2;
+        dim3 block(32, TH2_TJ);
+        dim3 grid((unsigned)((c->n2 / V + 31) / 32), (unsigned)((c->n1 + TH2_TJ - 1) / TH2_TJ),
+                  (unsigned)((a.p_hi - a.p_lo + TH2_PLANES - 1) / TH2_PLANES));
+        ProfScope ps(c, PROF_THERMAL);
+        if (V == 4) {
+            if (nanfix) thermal_kernel_v2<FULL, true, 4><<<grid, block, 0, c->stream>>>(a);
+            else thermal_kernel_v2<FULL, false, 4><<<grid, block, 0, c->stream>>>(a);
+        } else {
+            if (nanfix) thermal_kernel_v2<FULL, true, 2><<<grid, block, 0, c->stream>>>(a);
+            else thermal_kernel_v2<FULL, false, 2><<<grid, block, 0, c->stream>>>(a);
+        }
+    } else {
+        dim3 block(TH_TK, TH_TJ);
+        dim3 grid((unsigned)((c->n2 + TH_TK - 1) / TH_TK), (unsigned)((c->n1 + TH_TJ - 1) / TH_TJ),
+                  (unsigned)((a.p_hi - a.p_lo + TH_PLANES - 1) / TH_PLANES));
         ProfScope ps(c, PROF_THERMAL);
         thermal_kernel<FULL><<<grid, block, 0, c->stream>>>(a);
     }
@@ -152,6 +274,8 @@ static int launch_thermal(cet_ctx *c, ThermalArgs &a)
         CET_CUDA(cudaMemcpyAsync(c->T2 + (int64_t)a.p_hi * plane, c->T + (int64_t)a.p_hi * plane,
                                  (size_t)(c->np - a.p_hi) * plane * 8, cudaMemcpyDeviceToDevice, c->stream));
     double *t = c->T; c->T = c->T2; c->T2 = t;
+    if (a.nan_to_num) c->T_finite = true;   // a pass skipped by the stop flag cannot be the first of a run
+    if (FULL) c->T_finite = false;          // the laser source term is caller data
     c->rates_valid = false; c->sweep_rates_valid = false;
     return 0;
 }

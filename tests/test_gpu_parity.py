@@ -36,7 +36,8 @@ def test_thermal_cet_golden_sequences(cet):
         assert T.dtype == np.float64 and T.flags.c_contiguous
 
 
-@pytest.mark.parametrize("shape", [(64, 64, 64), (5, 130, 33), (1, 1, 7), (2, 3, 1), (40, 17, 257)])
+@pytest.mark.parametrize("shape", [(64, 64, 64), (5, 130, 33), (1, 1, 7), (2, 3, 1), (40, 17, 257), (6, 10, 2),
+                                   (3, 5, 66), (9, 11, 130), (33, 20, 64), (4, 4, 4)])
 def test_thermal_cet_resident_vs_oracle(cet, oracle, shape):
     from cetkmc._config import thermal_params
     rng = np.random.default_rng(3)
