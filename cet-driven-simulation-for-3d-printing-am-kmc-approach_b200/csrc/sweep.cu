@@ -26,8 +26,8 @@
 // rebuild (rates_rows).
 // Slabs: a context with halo H >= 6 evaluates ghost sites to depth 4 and resolves claims to
 // depth 2, which is everything that can write an owned site; after the one halo exchange per
-// sweep (comm.cu) the rates of the evaluated ghost planes are rebuilt densely (4 planes per
-// side).  Plane sums are combined in a fixed order so the trajectory is independent of the
+// sweep (comm.cu) the rates of the evaluated ghost planes and of the two outermost owned planes
+// are rebuilt densely (6 planes per cut face).  Plane sums are combined in a fixed order so the trajectory is independent of the
 // number of slabs.
 #include "ctx.cuh"
 #include "reduce.cuh"
@@ -554,9 +554,12 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
                 ProfScope ps(c, PROF_HALO);
                 if (int rc = comm_halo_exchange(c, 1 | 2)) return rc;
             }
-            // the ghost planes now hold the owners' lattice: rebuild the rates evaluated there
-            if (int rc = rates_rows(c, R.eval_lo, R.own_lo)) return rc;
-            if (int rc = rates_rows(c, R.own_hi, R.eval_hi)) return rc;
+            // The ghost planes now hold the owners' lattice.  Events this slab could not resolve
+            // (write set reaching beyond ghost depth 2) may have changed ghost planes that the two
+            // outermost owned planes read, so the dense rebuild covers the evaluated ghost planes
+            // and those two owned planes on each cut face.
+            if (R.own_lo > R.eval_lo) if (int rc = rates_rows(c, R.eval_lo, R.own_lo + 2)) return rc;
+            if (R.eval_hi > R.own_hi) if (int rc = rates_rows(c, R.own_hi - 2, R.eval_hi)) return rc;
         }
         c->sweep_index++;
     }

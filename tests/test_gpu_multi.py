@@ -1,0 +1,23 @@
+"""GPU, >= 2 devices: the z-slab decomposed sublattice run reproduces the single-GPU run of the
+same global lattice bit for bit (scripts/check_slabs.py under torch.distributed.run)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("extra", [["--L", "48", "--sweeps", "10"], ["--L", "40", "--n0", "80", "--sweeps", "16", "--eps", "0.004"]])
+def test_slabs_match_single_gpu(cet, extra):
+    n = min(cet.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    port = 29600 + (os.getpid() % 300)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "scripts", "check_slabs.py")] + extra
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "SLAB CHECK PASSED" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
