@@ -72,14 +72,17 @@ __device__ __forceinline__ void nb_offsets_init(NbOffsets *t, int L)
 struct Nst { unsigned lo, hi; };
 __device__ __forceinline__ Nst neighbour_states32(const uint8_t *vox, int s, unsigned inb, const NbOffsets *t)
 {
+    // fully unrolled on purpose: 14 independent byte loads in flight at once (a rolled loop
+    // serialises them behind the OR that consumes each result); the body is a handful of instructions
+    unsigned b[14];
+#pragma unroll
+    for (int o = 0; o < 14; ++o) b[o] = (inb >> o & 1u) ? (unsigned)vox[s + t->lin[o]] & 15u : 0u;
     Nst n;
     n.lo = 0; n.hi = 0;
-#pragma unroll 1
-    for (int o = 0; o < 8; ++o)
-        if (inb >> o & 1u) n.lo |= (unsigned)(vox[s + t->lin[o]] & 15) << (4 * o);
-#pragma unroll 1
-    for (int o = 8; o < 14; ++o)
-        if (inb >> o & 1u) n.hi |= (unsigned)(vox[s + t->lin[o]] & 15) << (4 * (o - 8));
+#pragma unroll
+    for (int o = 0; o < 8; ++o) n.lo |= b[o] << (4 * o);
+#pragma unroll
+    for (int o = 8; o < 14; ++o) n.hi |= b[o] << (4 * (o - 8));
     return n;
 }
 __device__ __forceinline__ unsigned nib_nonzero32(unsigned x) { return (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u; }
@@ -113,7 +116,7 @@ __device__ __forceinline__ double occ_chunk(const Lat &g, const cet_rate_params 
                 if (slot_bit(zl, zh, o)) emp_nb |= 1u << o;
             emp_nb &= inb;
         }
-#pragma unroll 1
+#pragma unroll 2
         for (int o = 0; o < 14; ++o) {
             const bool on = emp_nb >> o & 1u;
             if (!__any_sync(0xffffffffu, on)) continue;
@@ -143,7 +146,7 @@ __device__ __forceinline__ double emp_chunk(const Lat &g, const cet_rate_params 
     double sum = q.nuc_rate;
     if (__any_sync(0xffffffffu, (att_l | att_h) != 0)) {
         const double sx = g.vx[s], sy = g.vy[s], sz = g.vz[s];
-#pragma unroll 1
+#pragma unroll 2
         for (int o = 0; o < 14; ++o) {
             const bool on = slot_bit(att_l, att_h, o);
             if (!__any_sync(0xffffffffu, on)) continue;

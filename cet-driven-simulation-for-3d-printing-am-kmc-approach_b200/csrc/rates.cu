@@ -115,10 +115,21 @@ __global__ void __launch_bounds__(RB_WARPS * 32) dirty_scan_kernel(const __grid_
         const int p = a.p_lo + row / L, j = row % L;
         const bool top = a.g.i_off + p == a.g.n0 - 1;
         const int rbase = (p * L + j) * L;
-        for (int k0 = 0; k0 < L; k0 += 32) {
-            const int k = k0 + lane;
-            const bool sel = k < L && a.stamp[rbase + k] == a.stamp_id;
-            if (!sel) continue;
+        const bool vec = (L % 4) == 0;                       // rows are then 16-byte aligned in the stamp array
+        for (int k0 = 0; k0 < L; k0 += 128) {
+            const int kb = k0 + 4 * lane;                    // this lane's four consecutive sites
+            uint32_t stv[4];
+            if (vec && kb + 3 < L) {
+                const uint4 v4 = *reinterpret_cast<const uint4 *>(a.stamp + rbase + kb);
+                stv[0] = v4.x; stv[1] = v4.y; stv[2] = v4.z; stv[3] = v4.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) stv[e] = kb + e < L ? a.stamp[rbase + kb + e] : ~a.stamp_id;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+            const int k = kb + e;
+            if (stv[e] != a.stamp_id) continue;
             const int st = vox_state(a.g.vox[rbase + k]);
             if (st != 0) {
                 if (top) a.dep_rate[j * L + k] = NAN;                   // occupied: no deposition event
@@ -130,6 +141,7 @@ __global__ void __launch_bounds__(RB_WARPS * 32) dirty_scan_kernel(const __grid_
                 const unsigned int q = atomicAdd(&c_emp, 1u);
                 if (q < RB_WARPS * 64) s_emp[q] = rbase + k;
                 else a.list_emp[atomicAdd(a.n_emp, 1u)] = rbase + k;
+            }
             }
         }
     }
@@ -149,18 +161,22 @@ __global__ void __launch_bounds__(RB_WARPS * 32) dirty_eval_kernel(const __grid_
     __shared__ NbOffsets nbt;
     const int L = a.g.L, LL = L * L;
     nb_offsets_init(&nbt, L);
-    const int lane = threadIdx.x & 31;
-    const int warp = blockIdx.x * RB_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * RB_WARPS;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int no = (int)*a.n_occ, ne = (int)*a.n_emp;
-    for (int c0 = warp * 32; c0 < no; c0 += nwarps * 32) {
-        const bool active = c0 + lane < no;
+    // blocked distribution: a CTA owns a contiguous run of each list (lists are in lattice order, so
+    // its warps work on adjacent rows and share neighbour rows through L1)
+    const int per_o = ((no + 31) / 32 + gridDim.x - 1) / gridDim.x * 32, per_e = ((ne + 31) / 32 + gridDim.x - 1) / gridDim.x * 32;
+    const int o_lo = blockIdx.x * per_o, o_hi = min(no, o_lo + per_o);
+    const int e_lo = blockIdx.x * per_e, e_hi = min(ne, e_lo + per_e);
+    for (int c0 = o_lo + wid * 32; c0 < o_hi; c0 += RB_WARPS * 32) {
+        const bool active = c0 + lane < o_hi;
         const int s = a.list_occ[active ? c0 + lane : c0];
         const int p = s / LL, j = (s / L) % L, k = s % L;
         const double sum = occ_chunk(a.g, a.P, &nbt, a.g.i_off + p, j, k, s, active);
         if (active) a.site_rate[s] = sum;
     }
-    for (int c0 = warp * 32; c0 < ne; c0 += nwarps * 32) {
-        const bool active = c0 + lane < ne;
+    for (int c0 = e_lo + wid * 32; c0 < e_hi; c0 += RB_WARPS * 32) {
+        const bool active = c0 + lane < e_hi;
         const int s = a.list_emp[active ? c0 + lane : c0];
         const int p = s / LL, j = (s / L) % L, k = s % L;
         const int i = a.g.i_off + p;
@@ -239,7 +255,7 @@ int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint32_t *stamp, uint
     const int nrows = (p_hi - p_lo) * (int)c->n1;
     dirty_scan_kernel<<<(nrows + RB_WARPS - 1) / RB_WARPS, RB_WARPS * 32, 0, c->stream>>>(a);
     CET_CUDA(cudaGetLastError());
-    dirty_eval_kernel<<<148 * 6, RB_WARPS * 32, 0, c->stream>>>(a);
+    dirty_eval_kernel<<<148 * 40, RB_WARPS * 32, 0, c->stream>>>(a);
     CET_CUDA(cudaGetLastError());
     return 0;
 }

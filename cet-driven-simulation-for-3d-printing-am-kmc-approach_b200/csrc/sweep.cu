@@ -523,7 +523,7 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
             a.records = (Record *)c->records; a.claim = c->claim;
             a.seed = sp->seed; a.sweep = (uint32_t)c->sweep_index;
             ProfScope ps(c, PROF_PICK);
-            sweep_pick_kernel<<<148 * 8, 128, 0, c->stream>>>(a);
+            sweep_pick_kernel<<<148 * 32, 128, 0, c->stream>>>(a);
         }
         CET_CUDA(cudaGetLastError());
         {
@@ -537,7 +537,7 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
             b.stamp_id = (uint32_t)(c->sweep_index + 1);      // stamps start at 0
             b.defect_fraction = sp->defect_fraction;
             ProfScope ps(c, PROF_APPLY);
-            sweep_apply_kernel<<<148 * 8, 128, 0, c->stream>>>(b);
+            sweep_apply_kernel<<<148 * 32, 128, 0, c->stream>>>(b);
         }
         CET_CUDA(cudaGetLastError());
         {
