@@ -104,6 +104,7 @@ SIGNATURES = {
     "cet_comm_destroy": [_VP],
     "cet_halo_exchange": [_VP, C.c_int],
     "cet_allreduce_f64": [_VP, _VP, C.c_int, C.c_int],
+    "cet_debug_nst_mismatches": [_VP, C.POINTER(_I64)],
     "cet_profile_enable": [_VP, C.c_int],
     "cet_profile_read": [_VP, C.c_int, C.POINTER(_F64), C.POINTER(_I64), C.c_int],
     "cet_timer_begin": [_VP],
@@ -370,6 +371,11 @@ class Context:
         v = np.ascontiguousarray(values, dtype=np.float64).copy()
         check(lib().cet_allreduce_f64(self._h, _ptr(v), v.size, op), "cet_allreduce_f64")
         return v
+
+    def nst_mismatches(self):
+        n = C.c_int64(0)
+        check(lib().cet_debug_nst_mismatches(self._h, C.byref(n)), "cet_debug_nst_mismatches")
+        return n.value
 
     def sweep_reset(self):
         check(lib().cet_sweep_reset(self._h), "cet_sweep_reset")

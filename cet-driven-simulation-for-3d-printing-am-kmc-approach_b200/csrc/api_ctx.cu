@@ -74,11 +74,70 @@ __global__ void orient_kernel(const double *__restrict__ theta, const double *__
         unit_vector(theta[q], phi[q], &vx[q], &vy[q], &vz[q]);
 }
 
+// nst[s] = packed states of the 14 neighbours of s (0 for neighbours outside the global lattice)
+__global__ void nst_build_kernel(const uint8_t *__restrict__ vox, uint64_t *nst, int L, int n0, int i_off, int p_lo,
+                                 int p_hi)
+{
+    const int64_t LL = (int64_t)L * L;
+    const int64_t n = (int64_t)(p_hi - p_lo) * LL;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = (int64_t)p_lo * LL + q;
+        const int p = (int)(s / LL), j = (int)((s / L) % L), k = (int)(s % L);
+        const unsigned inb = inbounds_mask(i_off + p, j, k, n0, L);
+        uint64_t w = 0;
+#pragma unroll
+        for (int o = 0; o < 14; ++o)
+            if (inb >> o & 1u)
+                w |= (uint64_t)(vox[s + ((int64_t)CET_NB_DI(o) * L + CET_NB_DJ(o)) * L + CET_NB_DK(o)] & 15) << (4 * o);
+        nst[s] = w;
+    }
+}
+
+__global__ void nst_check_kernel(const uint8_t *__restrict__ vox, const uint64_t *__restrict__ nst, int L, int n0,
+                                 int i_off, int p_lo, int p_hi, unsigned long long *bad)
+{
+    const int64_t LL = (int64_t)L * L;
+    const int64_t n = (int64_t)(p_hi - p_lo) * LL;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = (int64_t)p_lo * LL + q;
+        const int p = (int)(s / LL), j = (int)((s / L) % L), k = (int)(s % L);
+        const unsigned inb = inbounds_mask(i_off + p, j, k, n0, L);
+        uint64_t w = 0;
+#pragma unroll
+        for (int o = 0; o < 14; ++o)
+            if (inb >> o & 1u)
+                w |= (uint64_t)(vox[s + ((int64_t)CET_NB_DI(o) * L + CET_NB_DJ(o)) * L + CET_NB_DK(o)] & 15) << (4 * o);
+        if (nst[s] != w) atomicAdd(bad, 1ull);
+    }
+}
+
 static int grid_for(int64_t n, int block)
 {
     int64_t g = (n + block - 1) / block;
     const int64_t cap = 148 * 16;
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+int nst_build(cet_ctx *c, int p_lo, int p_hi)
+{
+    if (p_hi <= p_lo) return 0;
+    const int64_t n = (int64_t)(p_hi - p_lo) * c->plane;
+    nst_build_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->vox, c->nst, (int)c->n1, (int)c->n0,
+                                                               (int)(c->i_begin - c->halo), p_lo, p_hi);
+    CET_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int nst_ensure(cet_ctx *c)
+{
+    if (c->nst_valid) return 0;
+    // planes whose i +- 2 neighbours are stored locally or lie outside the global lattice
+    const int i_off = (int)(c->i_begin - c->halo), np = (int)c->np;
+    const int lo = i_off > 0 ? 2 : (i_off < 0 ? -i_off : 0);
+    const int hi = (i_off + np < c->n0) ? np - 2 : (int)(c->n0 - i_off < np ? c->n0 - i_off : np);
+    if (int rc = nst_build(c, lo, hi)) return rc;
+    c->nst_valid = true;
+    return 0;
 }
 
 int orient_update(cet_ctx *c, int64_t p_lo, int64_t p_hi)
@@ -136,6 +195,8 @@ static int create_common(cet_ctx **out, int device, int64_t n0, int64_t n1, int6
         CET_CUDA(cudaMalloc(&c->vx, c->nloc * sizeof(double)));
         CET_CUDA(cudaMalloc(&c->vy, c->nloc * sizeof(double)));
         CET_CUDA(cudaMalloc(&c->vz, c->nloc * sizeof(double)));
+        CET_CUDA(cudaMalloc(&c->nst, c->nloc * sizeof(uint64_t)));
+        CET_CUDA(cudaMemsetAsync(c->nst, 0, c->nloc * sizeof(uint64_t), c->stream));
         if (int rc = orient_update(c, 0, c->np)) return rc;
         CET_CUDA(cudaMalloc(&c->site_rate, c->nloc * sizeof(double)));
         CET_CUDA(cudaMemsetAsync(c->site_rate, 0, c->nloc * sizeof(double), c->stream));
@@ -211,7 +272,7 @@ int cet_destroy(cet_ctx *c)
     cet::DeviceGuard dg(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cet_comm_destroy(c);
-    void *ptrs[] = {c->vox, c->vox_prev, c->theta, c->phi, c->vx, c->vy, c->vz, c->T, c->T2, c->site_rate, c->dep_rate,
+    void *ptrs[] = {c->vox, c->vox_prev, c->theta, c->phi, c->vx, c->vy, c->vz, c->nst, c->T, c->T2, c->site_rate, c->dep_rate,
                     c->row_occ, c->row_emp, c->row_dep, c->row_depcnt, c->seg, c->total, c->q_top,
                     c->stage, c->kmc, c->d_py, c->d_np, c->d_sp, c->d_log, c->sweep, c->claim,
                     c->records, c->blk_sum, c->blk_max, c->plane_sum, c->stamp, c->dirty, c->fired};
@@ -269,6 +330,7 @@ int cet_upload(cet_ctx *c, const int64_t *state, const double *theta, const doub
         if (defects) { dd = (int64_t *)p; CET_CUDA(cudaMemcpyAsync(dd, defects, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream)); }
         pack_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(ds, dd, c->vox + off, n, bad);
         CET_CUDA(cudaGetLastError());
+        if (state) c->nst_valid = false;
         int hbad = 0;
         CET_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CET_CUDA(cudaStreamSynchronize(c->stream));
@@ -344,6 +406,7 @@ int cet_upload_packed(cet_ctx *c, const uint8_t *packed)
     cet::DeviceGuard dg(c->device);
     CET_CUDA(cudaMemcpyAsync(c->vox + c->owned_offset(), packed, (size_t)c->owned_sites(),
                              cudaMemcpyHostToDevice, c->stream));
+    c->nst_valid = false;
     CET_CUDA(cudaStreamSynchronize(c->stream));
     c->rates_valid = false; c->sweep_rates_valid = false;
     return 0;
@@ -395,6 +458,27 @@ int cet_counts(cet_ctx *c, int64_t counts[16])
     CET_CUDA(cudaMemcpyAsync(h, c->stage, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CET_CUDA(cudaStreamSynchronize(c->stream));
     for (int q = 0; q < 16; ++q) counts[q] = (int64_t)h[q];
+    return 0;
+}
+
+int cet_debug_nst_mismatches(cet_ctx *c, int64_t *n_bad)
+{
+    CET_REQUIRE(c && n_bad && c->cubic, "cet_debug_nst_mismatches: bad argument");
+    cet::DeviceGuard dg(c->device);
+    if (!c->nst_valid) { *n_bad = -1; return 0; }           // stale by declaration: nothing to check
+    const int i_off = (int)(c->i_begin - c->halo), np = (int)c->np;
+    const int lo = i_off > 0 ? 2 : (i_off < 0 ? -i_off : 0);
+    const int hi = (i_off + np < c->n0) ? np - 2 : (int)(c->n0 - i_off < np ? c->n0 - i_off : np);
+    if (int rc = ensure_stage(c, 8)) return rc;
+    CET_CUDA(cudaMemsetAsync(c->stage, 0, 8, c->stream));
+    const int64_t n = (int64_t)(hi - lo) * c->plane;
+    nst_check_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->vox, c->nst, (int)c->n1, (int)c->n0, i_off, lo, hi,
+                                                               (unsigned long long *)c->stage);
+    CET_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    CET_CUDA(cudaMemcpyAsync(&h, c->stage, 8, cudaMemcpyDeviceToHost, c->stream));
+    CET_CUDA(cudaStreamSynchronize(c->stream));
+    *n_bad = (int64_t)h;
     return 0;
 }
 

@@ -99,6 +99,7 @@ int comm_halo_exchange(cet_ctx *c, int fields)
         }
     }
     CET_NCCL(g_nccl.GroupEnd());
+    if (fields & 1) c->nst_valid = false;      // ghost states changed (cet_sweep_run repairs the cache itself)
     if (fields & 2) {          // orientation unit vectors of the refreshed ghost planes
         if (lower >= 0) if (int rc = orient_update(c, 0, H)) return rc;
         if (upper < c->world) if (int rc = orient_update(c, c->np - H, c->np)) return rc;

@@ -79,6 +79,8 @@ struct cet_ctx {
     uint8_t *vox = nullptr, *vox_prev = nullptr;
     double *theta = nullptr, *phi = nullptr, *T = nullptr, *T2 = nullptr;
     double *vx = nullptr, *vy = nullptr, *vz = nullptr;
+    uint64_t *nst = nullptr;          // neighbour-state cache (see site_rates.cuh); valid on planes with both i-neighbour pairs local
+    bool nst_valid = false;
     double *site_rate = nullptr, *dep_rate = nullptr;
     double *row_occ = nullptr, *row_emp = nullptr, *row_dep = nullptr, *seg = nullptr;
     int32_t *row_depcnt = nullptr;
@@ -128,7 +130,7 @@ struct cet_ctx {
     cet::Lat lat() const
     {
         cet::Lat g;
-        g.vox = vox; g.vx = vx; g.vy = vy; g.vz = vz; g.T = T;
+        g.vox = vox; g.nst = nst; g.vx = vx; g.vy = vy; g.vz = vz; g.T = T;
         g.L = (int)n1; g.n0 = (int)n0;
         g.i_off = (int)(i_begin - halo);
         return g;
@@ -139,7 +141,9 @@ struct cet_ctx {
 
 namespace cet {
 int ensure_stage(cet_ctx *c, size_t bytes);
-int orient_update(cet_ctx *c, int64_t p_lo, int64_t p_hi);   // v := unit_vector(theta, phi) on local planes
+int orient_update(cet_ctx *c, int64_t p_lo, int64_t p_hi);
+int nst_build(cet_ctx *c, int p_lo, int p_hi);     // rebuild the neighbour-state cache of local planes [p_lo, p_hi)
+int nst_ensure(cet_ctx *c);                          // ... of every plane it can be built for, if it is stale   // v := unit_vector(theta, phi) on local planes
 enum { PROF_DECIDE = 0, PROF_APPLY = 1, PROF_THERMAL = 2, PROF_RATES = 3, PROF_HALO = 4, PROF_STEP = 5, PROF_PICK = 6,
        PROF_REFRESH = 7, PROF_KINDS = 8 };
 // RAII span: records an event pair around a launch when profiling is on.

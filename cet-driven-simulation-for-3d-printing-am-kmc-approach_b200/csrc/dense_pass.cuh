@@ -95,11 +95,30 @@ __device__ __forceinline__ bool slot_bit(unsigned lo, unsigned hi, int o)
 
 // One chunk of up to 32 occupied sites, one per lane (warp-collective: all 32 lanes call it;
 // `active` false on padding lanes).  Returns the lane's diffusion-rate sum in slot order.
+// Packed neighbour states of site s.  GATHER=false: one load from the cache (dense rebuild).
+// GATHER=true: 14 byte loads from the lattice, and the cache entry is repaired (the refresh pass
+// visits exactly the sites whose neighbourhood changed, so the cache needs no atomics in apply).
+template <bool GATHER>
+__device__ __forceinline__ Nst site_nst(const Lat &g, const NbOffsets *nbt, int s, unsigned inb, bool active,
+                                        uint64_t *nst_out)
+{
+    Nst nst;
+    if (GATHER) {
+        nst = neighbour_states32(g.vox, s, inb, nbt);
+        if (active) nst_out[s] = (uint64_t)nst.lo | ((uint64_t)nst.hi << 32);
+    } else {
+        const uint64_t nw = g.nst[s];
+        nst.lo = (unsigned)nw; nst.hi = (unsigned)(nw >> 32);
+    }
+    return nst;
+}
+
+template <bool GATHER>
 __device__ __forceinline__ double occ_chunk(const Lat &g, const cet_rate_params &P, const NbOffsets *nbt, int i, int j,
-                                            int k, int s, bool active)
+                                            int k, int s, bool active, uint64_t *nst_out = nullptr)
 {
     const unsigned inb = inbounds_mask(i, j, k, g.n0, g.L);
-    const Nst nst = neighbour_states32(g.vox, s, inb, nbt);
+    const Nst nst = site_nst<GATHER>(g, nbt, s, inb, active, nst_out);
     const int n_bonds = __popc(nib_nonzero32(nst.lo)) + __popc(nib_nonzero32(nst.hi));
     const bool has_events = active && n_bonds != __popc(inb);        // an in-bounds neighbour is empty
     double sum = 0.0;
@@ -128,12 +147,14 @@ __device__ __forceinline__ double occ_chunk(const Lat &g, const cet_rate_params 
 
 // One chunk of up to 32 empty sites.  Returns the nucleation + attachment rate sum in slot order;
 // the deposition event (global top plane only) is reported separately.
+template <bool GATHER>
 __device__ __forceinline__ double emp_chunk(const Lat &g, const cet_rate_params &P, const NbOffsets *nbt, int i, int j,
-                                            int k, int s, bool active, bool *has_dep, double *dep)
+                                            int k, int s, bool active, bool *has_dep, double *dep,
+                                            uint64_t *nst_out = nullptr)
 {
     const int L = g.L;
     const unsigned inb = inbounds_mask(i, j, k, g.n0, L);
-    const Nst nst = neighbour_states32(g.vox, s, inb, nbt);
+    const Nst nst = site_nst<GATHER>(g, nbt, s, inb, active, nst_out);
     const unsigned re_l = nib_equals32(nst.lo, P.states_re), re_h = nib_equals32(nst.hi, P.states_re) & 0x00111111u;
     const unsigned c_l = nib_equals32(nst.lo, P.states_c), c_h = nib_equals32(nst.hi, P.states_c) & 0x00111111u;
     unsigned att_l = nib_equals32(nst.lo, P.states_w) | re_l | c_l;           // nibble-LSB set: slot offers an attachment
@@ -172,7 +193,7 @@ __device__ __forceinline__ void row_occupied(const Lat &g, const cet_rate_params
     for (int c0 = 0; c0 < w.n_occ; c0 += 32) {
         const bool active = c0 + lane < w.n_occ;
         const int k = w.occ[active ? c0 + lane : c0];
-        fn(k, occ_chunk(g, P, nbt, i, j, k, rbase + k, active), active);
+        fn(k, occ_chunk<false>(g, P, nbt, i, j, k, rbase + k, active), active);
     }
 }
 
@@ -187,7 +208,7 @@ __device__ __forceinline__ void row_empty(const Lat &g, const cet_rate_params &P
         const int k = w.emp[active ? c0 + lane : c0];
         bool has_dep;
         double dep;
-        const double sum = emp_chunk(g, P, nbt, i, j, k, rbase + k, active, &has_dep, &dep);
+        const double sum = emp_chunk<false>(g, P, nbt, i, j, k, rbase + k, active, &has_dep, &dep);
         fn(k, sum, has_dep, dep, active);
     }
 }

@@ -94,6 +94,7 @@ struct DirtyArgs {
     Lat g;
     cet_rate_params P;
     double *site_rate, *dep_rate;
+    uint64_t *nst;                    // cache entries of the refreshed sites are rewritten
     const uint32_t *stamp;
     uint32_t stamp_id;
     int p_lo, p_hi;
@@ -133,7 +134,12 @@ __global__ void __launch_bounds__(RB_WARPS * 32) dirty_scan_kernel(const __grid_
             const int st = vox_state(a.g.vox[rbase + k]);
             if (st != 0) {
                 if (top) a.dep_rate[j * L + k] = NAN;                   // occupied: no deposition event
-                if (st == a.P.defect_id) { a.site_rate[rbase + k] = 0.0; continue; }   // defect: no events
+                if (st == a.P.defect_id) {                               // defect: no events; repair its cache word here
+                    a.site_rate[rbase + k] = 0.0;
+                    const unsigned inb = inbounds_mask(a.g.i_off + p, j, k, a.g.n0, L);
+                    a.nst[rbase + k] = neighbour_states(a.g, rbase + k, inb);
+                    continue;
+                }
                 const unsigned int q = atomicAdd(&c_occ, 1u);
                 if (q < RB_WARPS * 64) s_occ[q] = rbase + k;
                 else a.list_occ[atomicAdd(a.n_occ, 1u)] = rbase + k;
@@ -172,7 +178,7 @@ __global__ void __launch_bounds__(RB_WARPS * 32) dirty_eval_kernel(const __grid_
         const bool active = c0 + lane < o_hi;
         const int s = a.list_occ[active ? c0 + lane : c0];
         const int p = s / LL, j = (s / L) % L, k = s % L;
-        const double sum = occ_chunk(a.g, a.P, &nbt, a.g.i_off + p, j, k, s, active);
+        const double sum = occ_chunk<true>(a.g, a.P, &nbt, a.g.i_off + p, j, k, s, active, a.nst);
         if (active) a.site_rate[s] = sum;
     }
     for (int c0 = e_lo + wid * 32; c0 < e_hi; c0 += RB_WARPS * 32) {
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(RB_WARPS * 32) dirty_eval_kernel(const __grid_
         const int i = a.g.i_off + p;
         bool has_dep;
         double dep;
-        const double sum = emp_chunk(a.g, a.P, &nbt, i, j, k, s, active, &has_dep, &dep);
+        const double sum = emp_chunk<true>(a.g, a.P, &nbt, i, j, k, s, active, &has_dep, &dep, a.nst);
         if (active) {
             a.site_rate[s] = sum;
             if (i == a.g.n0 - 1) a.dep_rate[j * L + k] = has_dep ? dep : NAN;
@@ -218,6 +224,7 @@ int rates_rows(cet_ctx *c, int p_lo, int p_hi)
     CET_REQUIRE(c->cubic, "rates: context was created with cet_create_shape (thermal only)");
     CET_REQUIRE(c->have_rp, "rates: cet_set_rate_params has not been called");
     if (p_hi <= p_lo) return 0;
+    if (int rc = nst_ensure(c)) return rc;
     RatesArgs a;
     a.g = c->lat();
     a.P = c->rp;
@@ -245,10 +252,11 @@ int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint32_t *stamp, uint
                      unsigned int *counters)
 {
     if (p_hi <= p_lo) return 0;
+    if (int rc = nst_ensure(c)) return rc;
     DirtyArgs a;
     a.g = c->lat();
     a.P = c->rp;
-    a.site_rate = c->site_rate; a.dep_rate = c->dep_rate;
+    a.site_rate = c->site_rate; a.dep_rate = c->dep_rate; a.nst = c->nst;
     a.stamp = stamp; a.stamp_id = stamp_id; a.p_lo = p_lo; a.p_hi = p_hi;
     a.list_occ = lists; a.list_emp = lists + c->nloc;
     a.n_occ = counters; a.n_emp = counters + 1;
@@ -411,7 +419,7 @@ int cet_rates_total(cet_ctx *c, double *total, int64_t *n_dep)
 int cet_rates_download(cet_ctx *c, double *site_rate, double *dep_rate)
 {
     CET_REQUIRE(c, "cet_rates_download: NULL ctx");
-    CET_REQUIRE(c->rates_valid, "cet_rates_download: rates are stale (call cet_rates_build)");
+    CET_REQUIRE(c->rates_valid || c->sweep_rates_valid, "cet_rates_download: rates are stale (call cet_rates_build)");
     cet::DeviceGuard dg(c->device);
     if (site_rate)
         CET_CUDA(cudaMemcpyAsync(site_rate, c->site_rate + c->owned_offset(), (size_t)c->owned_sites() * 8,

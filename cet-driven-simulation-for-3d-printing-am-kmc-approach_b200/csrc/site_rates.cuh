@@ -69,6 +69,9 @@ static __constant__ int8_t c_nb_off[14][3] = CET_NB_TABLE_INIT;
 #define CET_NB_TAB h_nb_off
 #endif
 
+// slot of the opposite offset: offset[CET_NB_OPP(o)] == -offset[o]
+#define CET_NB_OPP(o) ((o) < 4 ? 3 - (o) : (o) < 8 ? 11 - (o) : ((o) ^ 1))
+
 // Packed voxel byte: low nibble = state (0 empty, 1 W, 2 Re, 3 C, 4 defect), high nibble =
 // defects_mask value.
 CET_HD int vox_state(uint8_t v) { return v & 0x0F; }
@@ -77,6 +80,7 @@ CET_HD int vox_defects(uint8_t v) { return v >> 4; }
 // View of the lattice (or of one slab of it with ghost planes) in device memory.
 struct Lat {
     const uint8_t *vox;
+    const uint64_t *nst;   // packed states of the 14 neighbours, 4 bits per slot (maintained cache; dense kernels only)
     const double *vx, *vy, *vz, *T;
     int L;       // edge length of axes 1 and 2
     int n0;      // global number of planes along axis 0 (== L for the reference's cubic lattices)

@@ -298,6 +298,7 @@ struct ApplyArgs {
     unsigned int cap_fired;
     unsigned long long *claim;
     uint32_t *stamp;
+    unsigned long long *nst;
     cet_rate_params P;
     int L, n0, i_off, np;
     int c_lo, c_hi;        // local planes with complete claims
@@ -307,9 +308,10 @@ struct ApplyArgs {
     double defect_fraction;
 };
 
-// request a rate refresh of the site and of its neighbours: the refresh pass (rates_rows_dirty)
-// re-evaluates every site whose stamp carries this sweep's id
-__device__ __forceinline__ void mark_neighbourhood(const ApplyArgs &a, int site)
+// A site changed state: request a refresh of the site and of its neighbours.  The refresh pass
+// (rates.cu) re-evaluates every site whose stamp carries this sweep's id and rewrites its cached
+// neighbour-state word — exactly the sites whose neighbourhood changed.
+__device__ __forceinline__ void site_changed(const ApplyArgs &a, int site, int, int)
 {
     const int LL = a.L * a.L;
     const int p = site / LL, j = (site / a.L) % a.L, k = site % a.L;
@@ -320,7 +322,8 @@ __device__ __forceinline__ void mark_neighbourhood(const ApplyArgs &a, int site)
         if (!(inb >> o & 1u)) continue;
         const int pn = p + c_nb_off[o][0];
         if (pn < 0 || pn >= a.np) continue;                             // ... and inside the local planes
-        a.stamp[site + (c_nb_off[o][0] * a.L + c_nb_off[o][1]) * a.L + c_nb_off[o][2]] = a.stamp_id;
+        const int n = site + (c_nb_off[o][0] * a.L + c_nb_off[o][1]) * a.L + c_nb_off[o][2];
+        a.stamp[n] = a.stamp_id;
     }
 }
 
@@ -351,6 +354,7 @@ __global__ void __launch_bounds__(128) sweep_apply_kernel(const __grid_constant_
         const bool win = complete && cs == key && ct == key;
         if (win) {
             int upd = s;
+            const int src_state = a.vox[s] & 0x0F;                      // before the event
             double ux, uy, uz;
             unit_vector(rec.theta, rec.phi, &ux, &uy, &uz);          // same bits as the source's resident vector
             if (ety == CET_EV_DIFF) {                                    // kmc_simulation.py:292-303
@@ -367,6 +371,7 @@ __global__ void __launch_bounds__(128) sweep_apply_kernel(const __grid_constant_
                 a.vx[s] = ux; a.vy[s] = uy; a.vz[s] = uz;
                 if (ety == CET_EV_NUC && owned) ++nuc;
             }
+            int upd_state = ety == CET_EV_DIFF ? src_state : eatom;      // what the filled site holds
             if (a.defect_fraction > 0.0) {                               // :323-327
                 double u2, unused;
                 philox_u2(a.seed, (uint64_t)gsite, a.sweep, STREAM_DEFECT, &u2, &unused);
@@ -374,11 +379,16 @@ __global__ void __launch_bounds__(128) sweep_apply_kernel(const __grid_constant_
                     a.vox[upd] = (uint8_t)((a.vox[upd] & 0xF0) | a.P.defect_id);
                     a.theta[upd] = 0.0; a.phi[upd] = 0.0;
                     a.vx[upd] = 0.0; a.vy[upd] = 0.0; a.vz[upd] = 1.0;
+                    upd_state = a.P.defect_id;
                 }
             }
             if (owned) ++applied;
-            mark_neighbourhood(a, s);
-            if (ety == CET_EV_DIFF) mark_neighbourhood(a, tgt);
+            if (ety == CET_EV_DIFF) {
+                site_changed(a, s, src_state, 0);
+                site_changed(a, tgt, 0, upd_state);
+            } else {
+                site_changed(a, s, 0, upd_state);
+            }
         }
         // release the claims this event holds (only the top claimant of a site clears it)
         if (cs == key) a.claim[s] = 0ull;
@@ -486,6 +496,7 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
     CET_CUDA(cudaMemcpyAsync(&before, c->sweep, sizeof(before), cudaMemcpyDeviceToHost, c->stream));
     CET_CUDA(cudaStreamSynchronize(c->stream));
 
+    if (int rc = nst_ensure(c)) return rc;        // the apply kernel maintains the cache from here on
     for (int64_t n = 0; n < n_sweeps; ++n) {
         ProfScope step_scope(c, PROF_STEP);
         if (sp->thermal_every > 0 && c->sweep_index % sp->thermal_every == 0) {
@@ -530,7 +541,7 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
             ApplyArgs b;
             b.vox = c->vox; b.theta = c->theta; b.phi = c->phi; b.vx = c->vx; b.vy = c->vy; b.vz = c->vz;
             b.ss = c->sweep; b.records = (const Record *)c->records; b.cap_fired = (unsigned int)c->cap_fired;
-            b.claim = c->claim; b.stamp = c->stamp;
+            b.claim = c->claim; b.stamp = c->stamp; b.nst = (unsigned long long *)c->nst;
             b.P = c->rp; b.L = (int)c->n1; b.n0 = (int)c->n0; b.i_off = i_off; b.np = (int)c->np;
             b.c_lo = R.claim_lo; b.c_hi = R.claim_hi; b.own_lo = R.own_lo; b.own_hi = R.own_hi;
             b.seed = sp->seed; b.sweep = (uint32_t)c->sweep_index;
@@ -558,8 +569,15 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
             // (write set reaching beyond ghost depth 2) may have changed ghost planes that the two
             // outermost owned planes read, so the dense rebuild covers the evaluated ghost planes
             // and those two owned planes on each cut face.
-            if (R.own_lo > R.eval_lo) if (int rc = rates_rows(c, R.eval_lo, R.own_lo + 2)) return rc;
-            if (R.eval_hi > R.own_hi) if (int rc = rates_rows(c, R.own_hi - 2, R.eval_hi)) return rc;
+            if (R.own_lo > R.eval_lo) {
+                if (int rc = nst_build(c, R.eval_lo, R.own_lo + 2)) return rc;
+                if (int rc = rates_rows(c, R.eval_lo, R.own_lo + 2)) return rc;
+            }
+            if (R.eval_hi > R.own_hi) {
+                if (int rc = nst_build(c, R.own_hi - 2, R.eval_hi)) return rc;
+                if (int rc = rates_rows(c, R.own_hi - 2, R.eval_hi)) return rc;
+            }
+            c->nst_valid = true;       // the exchange marked the cache stale; the two rebuilds above repaired it
         }
         c->sweep_index++;
     }

@@ -176,6 +176,10 @@ int cet_comm_destroy(cet_ctx *ctx);
 int cet_halo_exchange(cet_ctx *ctx, int fields);
 int cet_allreduce_f64(cet_ctx *ctx, double *inout_host, int n, int op /* 0 sum, 1 max */);
 
+/* Test hook: number of sites whose cached neighbour-state word differs from a fresh gather
+ * (-1 when the cache is declared stale). */
+int cet_debug_nst_mismatches(cet_ctx *ctx, int64_t *n_bad);
+
 /* ---- per-kernel device timing: CUDA event pairs recorded on the context stream around every
  * launch of a kind while enabled.  kind: 0 sweep stream (fire decision), 1 sweep apply,
  * 2 thermal stencil, 3 dense rate kernel, 4 halo exchange, 5 whole sweep, 6 sweep pick,

@@ -31,6 +31,7 @@ def test_sweep_is_deterministic_and_consistent(cet):
         ctx, st, th, ph, T, df = _setup(cet, L)
         res = ctx.sweep_run(12, _sweep_params(cet, 11, L, defect_fraction=0.01), None)
         outs.append((res, ctx.download(state=True, theta=True, phi=True), ctx.counts()))
+        assert ctx.nst_mismatches() == 0          # the incrementally patched neighbour cache equals a fresh gather
         ctx.close()
     (r1, f1, c1), (r2, f2, c2) = outs
     assert r1 == r2 and r1["events_applied"] > 0 and r1["events_applied"] <= r1["events_fired"]
@@ -128,3 +129,22 @@ def test_level3_observables_vs_serial_oracle(cet, oracle):
     se = np.sqrt(obs_o.var(0, ddof=1) / n_seeds + obs_g.var(0, ddof=1) / n_seeds)
     tol = 4 * se + 0.03 * np.abs(mo) + 1e-9
     assert np.all(np.abs(mo - mg) <= tol), (mo, mg, tol)
+
+
+def test_resident_rates_equal_rebuild_after_sweeps(cet):
+    """Neighbour-rate refresh invariant: after N sweeps (thermal steps and defect injection
+    included) the resident rate sums and the cached neighbour words equal a dense rebuild bit for
+    bit."""
+    from cetkmc._config import thermal_params
+    L = 36
+    ctx, st, th, ph, T, df = _setup(cet, L)
+    res = ctx.sweep_run(9, _sweep_params(cet, 21, L, eps=0.01, p_max=0.2, defect_fraction=0.02, thermal_every=4),
+                        thermal_params(1e-6, nan_to_num=True))
+    assert res["events_applied"] > 100 and res["sites_refreshed"] > res["events_applied"]
+    sr1, dr1 = ctx.rates_download()          # resident arrays as the sweeps left them
+    assert ctx.nst_mismatches() == 0
+    ctx.rates_build()                        # dense rebuild from the lattice
+    sr2, dr2 = ctx.rates_download()
+    ctx.close()
+    np.testing.assert_array_equal(sr1, sr2)
+    np.testing.assert_array_equal(dr1, dr2)
