@@ -66,12 +66,11 @@ __global__ void counts_kernel(const uint8_t *__restrict__ vox, int64_t n, unsign
     if (threadIdx.x < 16 && h[threadIdx.x]) atomicAdd(&out[threadIdx.x], (unsigned long long)h[threadIdx.x]);
 }
 
-__global__ void orient_kernel(const double *__restrict__ theta, const double *__restrict__ phi, double *vx,
-                              double *vy, double *vz, int64_t n)
+__global__ void orient_kernel(const double *__restrict__ theta, const double *__restrict__ phi, Vec4 *v, int64_t n)
 {
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n;
          q += (int64_t)gridDim.x * blockDim.x)
-        unit_vector(theta[q], phi[q], &vx[q], &vy[q], &vz[q]);
+        v[q] = unit_vec4(theta[q], phi[q]);
 }
 
 // nst[s] = packed states of the 14 neighbours of s (0 for neighbours outside the global lattice)
@@ -144,8 +143,7 @@ int orient_update(cet_ctx *c, int64_t p_lo, int64_t p_hi)
 {
     if (p_hi <= p_lo) return 0;
     const int64_t off = p_lo * c->plane, n = (p_hi - p_lo) * c->plane;
-    orient_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->theta + off, c->phi + off, c->vx + off, c->vy + off,
-                                                            c->vz + off, n);
+    orient_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->theta + off, c->phi + off, c->v + off, n);
     CET_CUDA(cudaGetLastError());
     return 0;
 }
@@ -192,9 +190,7 @@ static int create_common(cet_ctx **out, int device, int64_t n0, int64_t n1, int6
         CET_CUDA(cudaMalloc(&c->phi, c->nloc * sizeof(double)));
         CET_CUDA(cudaMemsetAsync(c->theta, 0, c->nloc * sizeof(double), c->stream));
         CET_CUDA(cudaMemsetAsync(c->phi, 0, c->nloc * sizeof(double), c->stream));
-        CET_CUDA(cudaMalloc(&c->vx, c->nloc * sizeof(double)));
-        CET_CUDA(cudaMalloc(&c->vy, c->nloc * sizeof(double)));
-        CET_CUDA(cudaMalloc(&c->vz, c->nloc * sizeof(double)));
+        CET_CUDA(cudaMalloc(&c->v, c->nloc * sizeof(Vec4)));
         CET_CUDA(cudaMalloc(&c->nst, c->nloc * sizeof(uint64_t)));
         CET_CUDA(cudaMemsetAsync(c->nst, 0, c->nloc * sizeof(uint64_t), c->stream));
         if (int rc = orient_update(c, 0, c->np)) return rc;
@@ -272,7 +268,7 @@ int cet_destroy(cet_ctx *c)
     cet::DeviceGuard dg(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cet_comm_destroy(c);
-    void *ptrs[] = {c->vox, c->vox_prev, c->theta, c->phi, c->vx, c->vy, c->vz, c->nst, c->T, c->T2, c->site_rate, c->dep_rate,
+    void *ptrs[] = {c->vox, c->vox_prev, c->theta, c->phi, c->v, c->nst, c->T, c->T2, c->site_rate, c->dep_rate,
                     c->row_occ, c->row_emp, c->row_dep, c->row_depcnt, c->seg, c->total, c->q_top,
                     c->stage, c->kmc, c->d_py, c->d_np, c->d_sp, c->d_log, c->sweep, c->claim,
                     c->records, c->blk_sum, c->blk_max, c->plane_sum, c->stamp, c->dirty, c->fired};
@@ -433,9 +429,7 @@ int cet_device_ptr(cet_ctx *c, int which, void **ptr, int64_t *nbytes)
         case 2: p = c->phi; nb = c->nloc * 8; break;
         case 3: p = c->T; nb = c->nloc * 8; break;
         case 4: p = c->site_rate; nb = c->nloc * 8; break;
-        case 5: p = c->vx; nb = c->nloc * 8; break;
-        case 6: p = c->vy; nb = c->nloc * 8; break;
-        case 7: p = c->vz; nb = c->nloc * 8; break;
+        case 5: p = c->v; nb = c->nloc * 32; break;
         default: set_error("cet_device_ptr: unknown field %d", which); return 1;
     }
     CET_REQUIRE(p != nullptr, "cet_device_ptr: field %d not allocated for this context", which);

@@ -55,7 +55,7 @@ struct SweepState {
 //   vox        u8   np*n1*n2   state | defects<<4
 //   vox_prev   u8   np*n1*n2   snapshot for the latent-heat term (allocated on first use)
 //   theta,phi  f64  np*n1*n2
-//   vx,vy,vz   f64  np*n1*n2   orientation unit vectors (derived from theta/phi; kept in step by every
+//   v          4xf64 np*n1*n2  orientation unit vectors, one 32-byte record per site (derived from theta/phi; kept in step by every
 //                              writer of theta/phi so the rate kernels never call sin/cos)
 //   T, T2      f64  np*n1*n2   ping-pong buffers of the thermal stencil
 //   site_rate  f64  np*n1*n2   sum of the site's diff (occupied) or nuc+att (empty) rates
@@ -78,7 +78,7 @@ struct cet_ctx {
 
     uint8_t *vox = nullptr, *vox_prev = nullptr;
     double *theta = nullptr, *phi = nullptr, *T = nullptr, *T2 = nullptr;
-    double *vx = nullptr, *vy = nullptr, *vz = nullptr;
+    cet::Vec4 *v = nullptr;
     uint64_t *nst = nullptr;          // neighbour-state cache (see site_rates.cuh); valid on planes with both i-neighbour pairs local
     bool nst_valid = false;
     double *site_rate = nullptr, *dep_rate = nullptr;
@@ -130,7 +130,7 @@ struct cet_ctx {
     cet::Lat lat() const
     {
         cet::Lat g;
-        g.vox = vox; g.nst = nst; g.vx = vx; g.vy = vy; g.vz = vz; g.T = T;
+        g.vox = vox; g.nst = nst; g.v = v; g.T = T;
         g.L = (int)n1; g.n0 = (int)n0;
         g.i_off = (int)(i_begin - halo);
         return g;

@@ -166,7 +166,8 @@ __device__ __forceinline__ double emp_chunk(const Lat &g, const cet_rate_params 
                                __popc(re_l) + __popc(re_h) + __popc(c_l) + __popc(c_h), __popc(inb));
     double sum = q.nuc_rate;
     if (__any_sync(0xffffffffu, (att_l | att_h) != 0)) {
-        const double sx = g.vx[s], sy = g.vy[s], sz = g.vz[s];
+        const Vec4 sv = g.v[s];
+        const double sx = sv.x, sy = sv.y, sz = sv.z;
 #pragma unroll 2
         for (int o = 0; o < 14; ++o) {
             const bool on = slot_bit(att_l, att_h, o);
@@ -174,7 +175,8 @@ __device__ __forceinline__ double emp_chunk(const Lat &g, const cet_rate_params 
             if (on) {
                 const int t = s + nbt->lin[o];
                 const int ia = slot_bit(re_l, re_h, o) ? 1 : (slot_bit(c_l, c_h, o) ? 2 : 0);
-                sum += att_pair_rate(P, q, ia, sx, sy, sz, g.vx[t], g.vy[t], g.vz[t]);
+                const Vec4 nv = g.v[t];
+                sum += att_pair_rate(P, q, ia, sx, sy, sz, nv.x, nv.y, nv.z);
             }
         }
     }

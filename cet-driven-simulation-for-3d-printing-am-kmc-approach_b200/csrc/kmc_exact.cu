@@ -27,7 +27,8 @@ constexpr int KX_MAX_AFFECTED = 32;
 
 struct KmcArgs {
     uint8_t *vox;
-    double *theta, *phi, *vx, *vy, *vz;
+    double *theta, *phi;
+    Vec4 *v;
     const double *T;
     double *site_rate, *dep_rate, *row_occ, *row_emp, *row_dep, *seg, *total;
     int32_t *row_depcnt;
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(KX_THREADS) kmc_steps_kernel(const KmcArgs a)
     const int L = a.L, LL = L * L;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = KX_THREADS / 32;
     Lat g;
-    g.vox = a.vox; g.vx = a.vx; g.vy = a.vy; g.vz = a.vz; g.T = a.T; g.L = L; g.n0 = L; g.i_off = 0;
+    g.vox = a.vox; g.v = a.v; g.T = a.T; g.L = L; g.n0 = L; g.i_off = 0;
     const bool use_u2 = a.defect_fraction > 0.0;
     const int py_per_step = use_u2 ? 3 : 2;
 
@@ -156,24 +157,24 @@ __global__ void __launch_bounds__(KX_THREADS) kmc_steps_kernel(const KmcArgs a)
                 const double th = __dadd_rn(0.0, __dmul_rn(3.141592653589793 - 0.0, ut));
                 const double ph = __dadd_rn(0.0, __dmul_rn(2 * 3.141592653589793 - 0.0, up));
                 a.theta[s] = th; a.phi[s] = ph;
-                unit_vector(th, ph, &a.vx[s], &a.vy[s], &a.vz[s]);
+                a.v[s] = unit_vec4(th, ph);
                 if (ety == CET_EV_NUC) ks->nucleation_count++;
                 sh.changed[0] = s; sh.n_changed = 1;
             } else if (ety == CET_EV_DIFF) {                               // :292-303
                 tgt = s + CET_NB_DI(eslot) * LL + CET_NB_DJ(eslot) * L + CET_NB_DK(eslot);
                 a.vox[tgt] = (uint8_t)((a.vox[tgt] & 0xF0) | (a.vox[s] & 0x0F));
                 a.theta[tgt] = a.theta[s]; a.phi[tgt] = a.phi[s];
-                a.vx[tgt] = a.vx[s]; a.vy[tgt] = a.vy[s]; a.vz[tgt] = a.vz[s];
+                a.v[tgt] = a.v[s];
                 a.vox[s] = (uint8_t)(a.vox[s] & 0xF0);
                 a.theta[s] = 0.0; a.phi[s] = 0.0;
-                a.vx[s] = 0.0; a.vy[s] = 0.0; a.vz[s] = 1.0;
+                a.v[s] = Vec4{0.0, 0.0, 1.0, 0.0};
                 upd = tgt;
                 sh.changed[0] = s; sh.changed[1] = tgt; sh.n_changed = 2;
             } else {                                                       // att :312-317
                 tgt = s + CET_NB_DI(eslot) * LL + CET_NB_DJ(eslot) * L + CET_NB_DK(eslot);
                 a.vox[s] = (uint8_t)((a.vox[s] & 0xF0) | eatom);
                 a.theta[s] = a.theta[tgt]; a.phi[s] = a.phi[tgt];
-                a.vx[s] = a.vx[tgt]; a.vy[s] = a.vy[tgt]; a.vz[s] = a.vz[tgt];
+                a.v[s] = a.v[tgt];
                 sh.changed[0] = s; sh.n_changed = 1;
             }
             if (use_u2) {                                                  // :323-327
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(KX_THREADS) kmc_steps_kernel(const KmcArgs a)
                 if (u2 < a.defect_fraction) {
                     a.vox[upd] = (uint8_t)((a.vox[upd] & 0xF0) | a.P.defect_id);
                     a.theta[upd] = 0.0; a.phi[upd] = 0.0;
-                    a.vx[upd] = 0.0; a.vy[upd] = 0.0; a.vz[upd] = 1.0;
+                    a.v[upd] = Vec4{0.0, 0.0, 1.0, 0.0};
                 }
             }
             const double u3 = a.py[ks->py_pos++];                          // :331-332
@@ -342,7 +343,7 @@ extern "C" int cet_kmc_run(cet_ctx *c, int64_t step0, int64_t n_steps, double de
         }
         // pointers are re-read every run: the thermal step swaps the T ping-pong buffers
         a.vox = c->vox; a.theta = c->theta; a.phi = c->phi; a.T = c->T;
-        a.vx = c->vx; a.vy = c->vy; a.vz = c->vz;
+        a.v = c->v;
         a.site_rate = c->site_rate; a.dep_rate = c->dep_rate; a.row_occ = c->row_occ; a.row_emp = c->row_emp;
         a.row_dep = c->row_dep; a.row_depcnt = c->row_depcnt; a.seg = c->seg; a.total = c->total;
         a.n_steps = run;

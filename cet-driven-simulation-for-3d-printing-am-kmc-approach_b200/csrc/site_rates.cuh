@@ -77,11 +77,16 @@ static __constant__ int8_t c_nb_off[14][3] = CET_NB_TABLE_INIT;
 CET_HD int vox_state(uint8_t v) { return v & 0x0F; }
 CET_HD int vox_defects(uint8_t v) { return v >> 4; }
 
+// Orientation unit vector of a site, one 32-byte record (= one DRAM sector: a gathered neighbour
+// costs one sector instead of three with separate x/y/z arrays).  w is unused padding.
+struct alignas(32) Vec4 { double x, y, z, w; };
+
 // View of the lattice (or of one slab of it with ghost planes) in device memory.
 struct Lat {
     const uint8_t *vox;
     const uint64_t *nst;   // packed states of the 14 neighbours, 4 bits per slot (maintained cache; dense kernels only)
-    const double *vx, *vy, *vz, *T;
+    const Vec4 *v;
+    const double *T;
     int L;       // edge length of axes 1 and 2
     int n0;      // global number of planes along axis 0 (== L for the reference's cubic lattices)
     int i_off;   // global i of local plane 0
@@ -124,6 +129,13 @@ CET_HD void unit_vector(double theta, double phi, double *x, double *y, double *
 {
     const double st = sin(theta);
     *x = st * cos(phi); *y = st * sin(phi); *z = cos(theta);
+}
+CET_HD Vec4 unit_vec4(double theta, double phi)
+{
+    Vec4 v;
+    unit_vector(theta, phi, &v.x, &v.y, &v.z);
+    v.w = 0.0;
+    return v;
 }
 
 // Deposition rate of an empty top-plane site (kmc_event_rates.py:60-64).  Returns false when
@@ -282,14 +294,16 @@ CET_HD void site_events(const Lat &g, const cet_rate_params &P, int i, int j, in
     const EmpPrep q = emp_prep(P, g.T[s], g.T[s + (km - k)], g.T[s + (kp - k)], n_imp, n_in);
     if (q.nuc_rate != 0.0) emit((int)CET_EV_NUC, -1, q.nuc_rate, P.states_w);
     if (n_bonds == 0) return;
-    const double sx = g.vx[s], sy = g.vy[s], sz = g.vz[s];
+    const Vec4 sv = g.v[s];
+    const double sx = sv.x, sy = sv.y, sz = sv.z;
 #pragma unroll 1
     for (int o = 0; o < 14; ++o) {                               // :135-158
         const int na = (int)(nst >> (4 * o)) & 15;
         const int ia = species_index(P, na);
         if (na == 0 || ia < 0) continue;
         const int64_t t = g.nb(s, o);
-        const double rate = att_pair_rate(P, q, ia, sx, sy, sz, g.vx[t], g.vy[t], g.vz[t]);
+        const Vec4 nv = g.v[t];
+        const double rate = att_pair_rate(P, q, ia, sx, sy, sz, nv.x, nv.y, nv.z);
         if (rate != 0.0) emit((int)CET_EV_ATT, o, rate, na);
     }
 }

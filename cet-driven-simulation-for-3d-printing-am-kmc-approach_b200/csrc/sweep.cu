@@ -64,7 +64,7 @@ __device__ __forceinline__ void philox_u2(uint64_t seed, uint64_t site, uint32_t
     *u0 = (double)(a >> 11) * 1.1102230246251565e-16;
     *u1 = (double)(b >> 11) * 1.1102230246251565e-16;
 }
-enum { STREAM_FIRE = 0, STREAM_PICK = 1, STREAM_ANGLES = 2, STREAM_SPECIES = 3, STREAM_DEFECT = 4 };
+enum { STREAM_FIRE = 0, STREAM_PICK = 1, STREAM_ANGLES = 2, STREAM_SPECIES = 3, STREAM_DEFECT = 4, STREAM_FIRE_REST = 5 };
 
 struct Record {          // one fired event
     int32_t src;         // local linear index of the source site
@@ -82,8 +82,14 @@ __device__ __forceinline__ unsigned long long claim_key(int rank, long long gsit
     return ((unsigned long long)(125 - rank) << 48) | (unsigned long long)(gsite + 1);
 }
 
-// ---- stream: one uniform per site against the resident rate sum --------------------------------
-constexpr int ST_THREADS = 256, ST_PER_THREAD = 4, ST_TILE = ST_THREADS * ST_PER_THREAD;
+// ---- stream: one fire test per site against the resident rate sum --------------------------------
+// HBM-bound by design: 8 B/site and ~14 instructions/site.  One Philox4x32-10 block (128 bits)
+// serves the 16 sites of a thread, 8 bits each, as the leading digit of the site's uniform in base
+// 256: with x = R*tau and p = 1-exp(-x) <= x the site can only fire if digit <= floor(256 x), which
+// rejects all but ~1/256 + p of the sites after three fp64 instructions; the survivors evaluate p
+// exactly and, when digit == floor(256 p), draw the remaining digits from a second Philox block.
+// P(fire) = floor(256 p)/256 + (1/256) P(u' < frac(256 p)) = p exactly.
+constexpr int ST_THREADS = 256, ST_PER_THREAD = 16, ST_TILE = ST_THREADS * ST_PER_THREAD;
 
 struct StreamArgs {
     const double *site_rate, *dep_rate;   // dep_rate: plane of the global top (NaN = no event)
@@ -100,7 +106,19 @@ struct StreamArgs {
     uint32_t sweep;
 };
 
-__global__ void __launch_bounds__(ST_THREADS) sweep_stream_kernel(const __grid_constant__ StreamArgs a)
+// The rare exact test of a site that survived the digit pre-filter (kept out of line: it holds an
+// expm1 and a second Philox block, and inlining it costs the streaming loop its occupancy).
+__device__ __noinline__ bool stream_fire_exact(double x, double d, uint64_t seed, uint64_t gsite, uint32_t sweep)
+{
+    const double p256 = -expm1(-x) * 256.0;
+    const double f = floor(p256);
+    if (d != f) return d < f;
+    double u_rest, unused;                              // leading digit ties: the rest of the uniform decides
+    philox_u2(seed, gsite, sweep, STREAM_FIRE_REST, &u_rest, &unused);
+    return u_rest < p256 - f;
+}
+
+__global__ void __launch_bounds__(ST_THREADS, 4) sweep_stream_kernel(const __grid_constant__ StreamArgs a)
 {
     __shared__ double s_sum[ST_THREADS / 32], s_max[ST_THREADS / 32];
     __shared__ int s_list[ST_TILE];                 // fired sites of this tile (appended with one global atomic)
@@ -109,42 +127,54 @@ __global__ void __launch_bounds__(ST_THREADS) sweep_stream_kernel(const __grid_c
     __syncthreads();
     const int pl = blockIdx.x / a.tiles_per_plane, tile = blockIdx.x % a.tiles_per_plane;
     const int p = a.p_lo + pl;
-    const int q0 = tile * ST_TILE + threadIdx.x * ST_PER_THREAD;      // first site of this thread in the plane
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const double tau = a.ss->terminated ? 0.0 : a.ss->tau;
-    double R[ST_PER_THREAD];
     const int64_t base = (int64_t)p * a.plane_sites;
-    const bool vec = (a.plane_sites % ST_PER_THREAD) == 0;           // every plane then starts 32-byte aligned
-    if (vec && q0 + ST_PER_THREAD <= a.plane_sites) {
-        const double2 *src = reinterpret_cast<const double2 *>(a.site_rate + base + q0);
-        const double2 v0 = src[0], v1 = src[1];
-        R[0] = v0.x; R[1] = v0.y; R[2] = v1.x; R[3] = v1.y;
-    } else {
+    // site e of this thread: pairs interleaved across the warp so that every load is a coalesced
+    // 512-byte warp access: q(e) = tile*ST_TILE + w*512 + (e/2)*64 + lane*2 + (e&1)
+    const int qw = tile * ST_TILE + w * (32 * ST_PER_THREAD) + lane * 2;
+    double R[ST_PER_THREAD];
+    const bool vec = (a.plane_sites & 1) == 0;                       // every plane then starts 16-byte aligned
 #pragma unroll
-        for (int e = 0; e < ST_PER_THREAD; ++e) R[e] = q0 + e < a.plane_sites ? a.site_rate[base + q0 + e] : 0.0;
+    for (int m = 0; m < ST_PER_THREAD / 2; ++m) {
+        const int q = qw + m * 64;
+        if (vec && q + 1 < a.plane_sites) {
+            const double2 v = *reinterpret_cast<const double2 *>(a.site_rate + base + q);
+            R[2 * m] = v.x; R[2 * m + 1] = v.y;
+        } else {
+            R[2 * m] = q < a.plane_sites ? a.site_rate[base + q] : 0.0;
+            R[2 * m + 1] = q + 1 < a.plane_sites ? a.site_rate[base + q + 1] : 0.0;
+        }
     }
     if (p == a.top_plane) {
 #pragma unroll
-        for (int e = 0; e < ST_PER_THREAD; ++e)
-            if (q0 + e < a.plane_sites) {
-                const double d = a.dep_rate[q0 + e];
+        for (int e = 0; e < ST_PER_THREAD; ++e) {
+            const int q = qw + (e >> 1) * 64 + (e & 1);
+            if (q < a.plane_sites) {
+                const double d = a.dep_rate[q];
                 if (d == d) R[e] = d + R[e];
             }
+        }
     }
     double rsum = 0.0, rmax = 0.0;
 #pragma unroll
     for (int e = 0; e < ST_PER_THREAD; ++e) { rsum += R[e]; rmax = fmax(rmax, R[e]); }
     if (tau > 0.0 && rmax > 0.0) {
-        // one Philox block serves the four sites of this thread: 32 random bits per fire test
-        const u32x4 r = philox4x32_10(u32x4{(uint32_t)(q0 >> 2), (uint32_t)(a.i_off + p), a.sweep, (uint32_t)STREAM_FIRE},
+        const uint32_t tid_in_plane = (uint32_t)(tile * ST_THREADS + threadIdx.x);
+        const u32x4 r = philox4x32_10(u32x4{tid_in_plane, (uint32_t)(a.i_off + p), a.sweep, (uint32_t)STREAM_FIRE},
                                       (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-        const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
+        const uint32_t words[4] = {r.x, r.y, r.z, r.w};
+        const double tau256 = tau * 256.0;
 #pragma unroll
         for (int e = 0; e < ST_PER_THREAD; ++e) {
-            const double u = ((double)bits[e] + 0.5) * 2.3283064365386963e-10;      // (0,1), 32 bits
-            const double x = R[e] * tau;
-            if (u < x && u < -expm1(-x))                      // 1 - exp(-x) <= x: most sites stop at the first test
-                s_list[atomicAdd(&s_cnt, 1u)] = (int32_t)(base + q0 + e);
+            const uint32_t digit = (words[e >> 2] >> (8 * (e & 3))) & 0xFFu;
+            const double d = __hiloint2double(0x43300000, (int)digit) - 4503599627370496.0;   // (double)digit
+            const double x256 = R[e] * tau256;
+            if (d > x256) continue;                             // digit > floor(256 x) >= floor(256 p): cannot fire
+            const int q = qw + (e >> 1) * 64 + (e & 1);
+            if (stream_fire_exact(R[e] * tau, d, a.seed, (uint64_t)(a.i_off + p) * (uint64_t)a.plane_sites + (uint64_t)q,
+                                  a.sweep))
+                s_list[atomicAdd(&s_cnt, 1u)] = (int32_t)(base + q);
         }
     }
     rsum = warp_sum(rsum);
@@ -292,7 +322,8 @@ __global__ void sweep_finalize_kernel(SweepState *ss, const double *plane_sum, i
 // ---- apply ---------------------------------------------------------------------------------------
 struct ApplyArgs {
     uint8_t *vox;
-    double *theta, *phi, *vx, *vy, *vz;
+    double *theta, *phi;
+    Vec4 *v;
     SweepState *ss;
     const Record *records;
     unsigned int cap_fired;
@@ -355,20 +386,19 @@ __global__ void __launch_bounds__(128) sweep_apply_kernel(const __grid_constant_
         if (win) {
             int upd = s;
             const int src_state = a.vox[s] & 0x0F;                      // before the event
-            double ux, uy, uz;
-            unit_vector(rec.theta, rec.phi, &ux, &uy, &uz);          // same bits as the source's resident vector
+            const Vec4 uv = unit_vec4(rec.theta, rec.phi);             // same bits as the source's resident vector
             if (ety == CET_EV_DIFF) {                                    // kmc_simulation.py:292-303
                 a.vox[tgt] = (uint8_t)((a.vox[tgt] & 0xF0) | (a.vox[s] & 0x0F));
                 a.theta[tgt] = rec.theta; a.phi[tgt] = rec.phi;
-                a.vx[tgt] = ux; a.vy[tgt] = uy; a.vz[tgt] = uz;
+                a.v[tgt] = uv;
                 a.vox[s] = (uint8_t)(a.vox[s] & 0xF0);
                 a.theta[s] = 0.0; a.phi[s] = 0.0;
-                a.vx[s] = 0.0; a.vy[s] = 0.0; a.vz[s] = 1.0;
+                a.v[s] = Vec4{0.0, 0.0, 1.0, 0.0};
                 upd = tgt;
             } else {                                                     // dep / nuc / att
                 a.vox[s] = (uint8_t)((a.vox[s] & 0xF0) | eatom);
                 a.theta[s] = rec.theta; a.phi[s] = rec.phi;
-                a.vx[s] = ux; a.vy[s] = uy; a.vz[s] = uz;
+                a.v[s] = uv;
                 if (ety == CET_EV_NUC && owned) ++nuc;
             }
             int upd_state = ety == CET_EV_DIFF ? src_state : eatom;      // what the filled site holds
@@ -378,7 +408,7 @@ __global__ void __launch_bounds__(128) sweep_apply_kernel(const __grid_constant_
                 if (u2 < a.defect_fraction) {
                     a.vox[upd] = (uint8_t)((a.vox[upd] & 0xF0) | a.P.defect_id);
                     a.theta[upd] = 0.0; a.phi[upd] = 0.0;
-                    a.vx[upd] = 0.0; a.vy[upd] = 0.0; a.vz[upd] = 1.0;
+                    a.v[upd] = Vec4{0.0, 0.0, 1.0, 0.0};
                     upd_state = a.P.defect_id;
                 }
             }
@@ -539,7 +569,7 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
         CET_CUDA(cudaGetLastError());
         {
             ApplyArgs b;
-            b.vox = c->vox; b.theta = c->theta; b.phi = c->phi; b.vx = c->vx; b.vy = c->vy; b.vz = c->vz;
+            b.vox = c->vox; b.theta = c->theta; b.phi = c->phi; b.v = c->v;
             b.ss = c->sweep; b.records = (const Record *)c->records; b.cap_fired = (unsigned int)c->cap_fired;
             b.claim = c->claim; b.stamp = c->stamp; b.nst = (unsigned long long *)c->nst;
             b.P = c->rp; b.L = (int)c->n1; b.n0 = (int)c->n0; b.i_off = i_off; b.np = (int)c->np;

@@ -125,7 +125,7 @@ int cet_snapshot_state(cet_ctx *ctx); /* prev_state := state, on device */
 int cet_upload_packed(cet_ctx *ctx, const uint8_t *packed);
 int cet_download_packed(cet_ctx *ctx, uint8_t *packed);
 /* Raw device pointers for tensor hand-off (torch.distributed halo exchange, tests).
- * which: 0 packed state, 1 theta, 2 phi, 3 T, 4 site_rate, 5/6/7 orientation unit vector x/y/z.  Pointer addresses local plane 0
+ * which: 0 packed state, 1 theta, 2 phi, 3 T, 4 site_rate, 5 orientation unit vectors (32-byte records x,y,z,pad).  Pointer addresses local plane 0
  * (ghost planes included); nbytes is the full extent. */
 int cet_device_ptr(cet_ctx *ctx, int which, void **ptr, int64_t *nbytes);
 int cet_counts(cet_ctx *ctx, int64_t counts[16]); /* histogram of state values, owned planes */

@@ -12,10 +12,10 @@ extern "C" long long hostsim_events(const uint8_t *vox, const double *theta, con
                                     long long *pos, double *rate, long long *target, int32_t *atom)
 {
     const long long LL = (long long)L * L;
-    std::vector<double> vx(LL * L), vy(LL * L), vz(LL * L);
-    for (long long q = 0; q < LL * L; ++q) unit_vector(theta[q], phi[q], &vx[q], &vy[q], &vz[q]);
+    std::vector<Vec4> v(LL * L);
+    for (long long q = 0; q < LL * L; ++q) v[q] = unit_vec4(theta[q], phi[q]);
     Lat g;
-    g.vox = vox; g.vx = vx.data(); g.vy = vy.data(); g.vz = vz.data(); g.T = T; g.L = L; g.n0 = L; g.i_off = 0;
+    g.vox = vox; g.v = v.data(); g.T = T; g.L = L; g.n0 = L; g.i_off = 0;
     long long n = 0;
     auto put = [&](int ty, long long s, double r, long long t, int a) {
         if (n < cap) { type[n] = (uint8_t)ty; pos[n] = s; rate[n] = r; target[n] = t; atom[n] = a; }
