@@ -95,7 +95,7 @@ struct DirtyArgs {
     cet_rate_params P;
     double *site_rate, *dep_rate;
     uint64_t *nst;                    // cache entries of the refreshed sites are rewritten
-    const uint32_t *stamp;
+    const uint8_t *stamp;
     uint32_t stamp_id;
     int p_lo, p_hi;
     int32_t *list_occ, *list_emp;     // capacity: one entry per local site
@@ -116,21 +116,37 @@ __global__ void __launch_bounds__(RB_WARPS * 32) dirty_scan_kernel(const __grid_
         const int p = a.p_lo + row / L, j = row % L;
         const bool top = a.g.i_off + p == a.g.n0 - 1;
         const int rbase = (p * L + j) * L;
-        const bool vec = (L % 4) == 0;                       // rows are then 16-byte aligned in the stamp array
-        for (int k0 = 0; k0 < L; k0 += 128) {
-            const int kb = k0 + 4 * lane;                    // this lane's four consecutive sites
-            uint32_t stv[4];
-            if (vec && kb + 3 < L) {
+        const bool vec = (L % 16) == 0;                      // rows are then 16-byte aligned in the stamp array
+        const uint8_t want = (uint8_t)a.stamp_id;
+        for (int k0 = 0; k0 < L; k0 += 512) {
+            const int kb = k0 + 16 * lane;                   // this lane's sixteen consecutive sites
+            if (kb >= L) continue;
+            uint32_t wv[4];
+            if (vec) {
                 const uint4 v4 = *reinterpret_cast<const uint4 *>(a.stamp + rbase + kb);
-                stv[0] = v4.x; stv[1] = v4.y; stv[2] = v4.z; stv[3] = v4.w;
+                wv[0] = v4.x; wv[1] = v4.y; wv[2] = v4.z; wv[3] = v4.w;
             } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) stv[e] = kb + e < L ? a.stamp[rbase + kb + e] : ~a.stamp_id;
+                for (int q = 0; q < 4; ++q) {
+                    wv[q] = 0;
+                    for (int b = 0; b < 4; ++b)
+                        if (kb + 4 * q + b < L) wv[q] |= (uint32_t)(a.stamp[rbase + kb + 4 * q + b] == want ? want : (uint8_t)~want) << (8 * b);
+                        else wv[q] |= (uint32_t)(uint8_t)~want << (8 * b);
+                }
             }
+            // one bit per matching byte (exact zero-byte test on wv ^ rep), then visit the matches only
+            const uint32_t rep = 0x01010101u * want;
+            uint32_t match = 0;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t x = wv[q] ^ rep;                                  // zero byte <=> match
+                const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 in every zero byte
+                match |= (((z >> 7) & 1u) | ((z >> 14) & 2u) | ((z >> 21) & 4u) | ((z >> 28) & 8u)) << (4 * q);
+            }
+            while (match) {
+            const int e = __ffs(match) - 1;
+            match &= match - 1;
             const int k = kb + e;
-            if (stv[e] != a.stamp_id) continue;
             const int st = vox_state(a.g.vox[rbase + k]);
             if (st != 0) {
                 if (top) a.dep_rate[j * L + k] = NAN;                   // occupied: no deposition event
@@ -248,7 +264,7 @@ int rates_rows(cet_ctx *c, int p_lo, int p_hi)
 
 // Re-evaluate, on local planes [p_lo, p_hi), the sites whose stamp equals stamp_id.
 // lists: 2 * nloc int32 (occupied list, then empty list); counters: two device unsigned ints (zeroed by the caller).
-int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint32_t *stamp, uint32_t stamp_id, int32_t *lists,
+int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint8_t *stamp, uint32_t stamp_id, int32_t *lists,
                      unsigned int *counters)
 {
     if (p_hi <= p_lo) return 0;

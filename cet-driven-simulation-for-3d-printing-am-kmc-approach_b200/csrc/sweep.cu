@@ -36,7 +36,7 @@ namespace cet {
 
 int thermal_cet_step(cet_ctx *c, const cet_thermal_params *p, const int32_t *stop_flag);
 int rates_rows(cet_ctx *c, int p_lo, int p_hi);                                  // rates.cu
-int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint32_t *stamp, uint32_t stamp_id, int32_t *lists,
+int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint8_t *stamp, uint32_t stamp_id, int32_t *lists,
                      unsigned int *counters);
 int comm_sweep_reduce(cet_ctx *c, double *plane_sum, int n, double *max_inout);   // comm.cu
 int comm_halo_exchange(cet_ctx *c, int fields);
@@ -89,7 +89,7 @@ __device__ __forceinline__ unsigned long long claim_key(int rank, long long gsit
 // rejects all but ~1/256 + p of the sites after three fp64 instructions; the survivors evaluate p
 // exactly and, when digit == floor(256 p), draw the remaining digits from a second Philox block.
 // P(fire) = floor(256 p)/256 + (1/256) P(u' < frac(256 p)) = p exactly.
-constexpr int ST_THREADS = 256, ST_PER_THREAD = 16, ST_TILE = ST_THREADS * ST_PER_THREAD;
+constexpr int ST_THREADS = 256, ST_PER_THREAD = 16, ST_TILE = ST_THREADS * ST_PER_THREAD, ST_SURV = 1024;
 
 struct StreamArgs {
     const double *site_rate, *dep_rate;   // dep_rate: plane of the global top (NaN = no event)
@@ -121,9 +121,13 @@ __device__ __noinline__ bool stream_fire_exact(double x, double d, uint64_t seed
 __global__ void __launch_bounds__(ST_THREADS, 4) sweep_stream_kernel(const __grid_constant__ StreamArgs a)
 {
     __shared__ double s_sum[ST_THREADS / 32], s_max[ST_THREADS / 32];
-    __shared__ int s_list[ST_TILE];                 // fired sites of this tile (appended with one global atomic)
-    __shared__ unsigned int s_cnt, s_base;
-    if (threadIdx.x == 0) s_cnt = 0;
+    // survivors of the pre-filter (beyond ST_SURV they are tested in place) and fired sites of this tile
+    __shared__ int s_surv_q[ST_SURV];
+    __shared__ double s_surv_x[ST_SURV];
+    __shared__ uint8_t s_surv_d[ST_SURV];
+    __shared__ int s_list[ST_TILE];
+    __shared__ unsigned int s_cnt, s_base, s_nsurv;
+    if (threadIdx.x == 0) { s_cnt = 0; s_nsurv = 0; }
     __syncthreads();
     const int pl = blockIdx.x / a.tiles_per_plane, tile = blockIdx.x % a.tiles_per_plane;
     const int p = a.p_lo + pl;
@@ -159,6 +163,7 @@ __global__ void __launch_bounds__(ST_THREADS, 4) sweep_stream_kernel(const __gri
     double rsum = 0.0, rmax = 0.0;
 #pragma unroll
     for (int e = 0; e < ST_PER_THREAD; ++e) { rsum += R[e]; rmax = fmax(rmax, R[e]); }
+    // stage 1: digit pre-filter; survivors (a few per cent) are queued for the exact test
     if (tau > 0.0 && rmax > 0.0) {
         const uint32_t tid_in_plane = (uint32_t)(tile * ST_THREADS + threadIdx.x);
         const u32x4 r = philox4x32_10(u32x4{tid_in_plane, (uint32_t)(a.i_off + p), a.sweep, (uint32_t)STREAM_FIRE},
@@ -169,17 +174,30 @@ __global__ void __launch_bounds__(ST_THREADS, 4) sweep_stream_kernel(const __gri
         for (int e = 0; e < ST_PER_THREAD; ++e) {
             const uint32_t digit = (words[e >> 2] >> (8 * (e & 3))) & 0xFFu;
             const double d = __hiloint2double(0x43300000, (int)digit) - 4503599627370496.0;   // (double)digit
-            const double x256 = R[e] * tau256;
-            if (d > x256) continue;                             // digit > floor(256 x) >= floor(256 p): cannot fire
-            const int q = qw + (e >> 1) * 64 + (e & 1);
-            if (stream_fire_exact(R[e] * tau, d, a.seed, (uint64_t)(a.i_off + p) * (uint64_t)a.plane_sites + (uint64_t)q,
-                                  a.sweep))
-                s_list[atomicAdd(&s_cnt, 1u)] = (int32_t)(base + q);
+            if (d <= R[e] * tau256) {                           // else digit > floor(256 x) >= floor(256 p): cannot fire
+                const unsigned int slot = atomicAdd(&s_nsurv, 1u);
+                const int site = qw + (e >> 1) * 64 + (e & 1);
+                if (slot < ST_SURV) {
+                    s_surv_q[slot] = site; s_surv_x[slot] = R[e] * tau; s_surv_d[slot] = (uint8_t)digit;
+                } else if (stream_fire_exact(R[e] * tau, d, a.seed,
+                                             (uint64_t)(a.i_off + p) * (uint64_t)a.plane_sites + (uint64_t)site, a.sweep)) {
+                    s_list[atomicAdd(&s_cnt, 1u)] = (int32_t)(base + site);
+                }
+            }
         }
     }
     rsum = warp_sum(rsum);
     rmax = warp_max(rmax);
     if (lane == 0) { s_sum[w] = rsum; s_max[w] = rmax; }
+    __syncthreads();
+    // stage 2: exact test of the survivors, converged
+    for (unsigned int q = threadIdx.x; q < min(s_nsurv, (unsigned)ST_SURV); q += ST_THREADS) {
+        const int site = s_surv_q[q];
+        const double d = (double)s_surv_d[q];
+        if (stream_fire_exact(s_surv_x[q], d, a.seed, (uint64_t)(a.i_off + p) * (uint64_t)a.plane_sites + (uint64_t)site,
+                              a.sweep))
+            s_list[atomicAdd(&s_cnt, 1u)] = (int32_t)(base + site);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0.0, m = 0.0;
@@ -328,7 +346,7 @@ struct ApplyArgs {
     const Record *records;
     unsigned int cap_fired;
     unsigned long long *claim;
-    uint32_t *stamp;
+    uint8_t *stamp;
     unsigned long long *nst;
     cet_rate_params P;
     int L, n0, i_off, np;
@@ -346,7 +364,7 @@ __device__ __forceinline__ void site_changed(const ApplyArgs &a, int site, int, 
 {
     const int LL = a.L * a.L;
     const int p = site / LL, j = (site / a.L) % a.L, k = site % a.L;
-    a.stamp[site] = a.stamp_id;
+    a.stamp[site] = (uint8_t)a.stamp_id;
     const unsigned inb = inbounds_mask(a.i_off + p, j, k, a.n0, a.L);    // inside the GLOBAL lattice ...
 #pragma unroll 1
     for (int o = 0; o < 14; ++o) {
@@ -354,7 +372,7 @@ __device__ __forceinline__ void site_changed(const ApplyArgs &a, int site, int, 
         const int pn = p + c_nb_off[o][0];
         if (pn < 0 || pn >= a.np) continue;                             // ... and inside the local planes
         const int n = site + (c_nb_off[o][0] * a.L + c_nb_off[o][1]) * a.L + c_nb_off[o][2];
-        a.stamp[n] = a.stamp_id;
+        a.stamp[n] = (uint8_t)a.stamp_id;
     }
 }
 
@@ -449,8 +467,8 @@ static int sweep_alloc(cet_ctx *c)
         CET_CUDA(cudaMemsetAsync(c->claim, 0, (size_t)c->nloc * sizeof(unsigned long long), c->stream));
     }
     if (!c->stamp) {
-        CET_CUDA(cudaMalloc(&c->stamp, (size_t)c->nloc * sizeof(uint32_t)));
-        CET_CUDA(cudaMemsetAsync(c->stamp, 0, (size_t)c->nloc * sizeof(uint32_t), c->stream));
+        CET_CUDA(cudaMalloc(&c->stamp, (size_t)c->nloc + 64));
+        CET_CUDA(cudaMemsetAsync(c->stamp, 0, (size_t)c->nloc + 64, c->stream));
     }
     if (!c->dirty) {
         c->cap_dirty = (size_t)c->nloc;               // occupied list + empty list, one entry per site each
@@ -537,6 +555,10 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
             if (int rc = rates_rows(c, R.eval_lo, R.eval_hi)) return rc;
             c->sweep_rates_valid = true;
         }
+        // one-byte stamps: ids cycle through 1..255, the array is cleared when the cycle restarts
+        const uint32_t stamp_id = (uint32_t)(c->stamp_cycle % 255) + 1;
+        if (stamp_id == 1) CET_CUDA(cudaMemsetAsync(c->stamp, 0, (size_t)c->nloc, c->stream));
+        c->stamp_cycle++;
         sweep_reset_kernel<<<1, 1, 0, c->stream>>>(c->sweep, max_slot);
         CET_CUDA(cudaMemsetAsync(c->plane_sum, 0, (size_t)c->n0 * sizeof(double), c->stream));
         {
@@ -575,7 +597,7 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
             b.P = c->rp; b.L = (int)c->n1; b.n0 = (int)c->n0; b.i_off = i_off; b.np = (int)c->np;
             b.c_lo = R.claim_lo; b.c_hi = R.claim_hi; b.own_lo = R.own_lo; b.own_hi = R.own_hi;
             b.seed = sp->seed; b.sweep = (uint32_t)c->sweep_index;
-            b.stamp_id = (uint32_t)(c->sweep_index + 1);      // stamps start at 0
+            b.stamp_id = stamp_id;
             b.defect_fraction = sp->defect_fraction;
             ProfScope ps(c, PROF_APPLY);
             sweep_apply_kernel<<<148 * 32, 128, 0, c->stream>>>(b);
@@ -583,7 +605,7 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
         CET_CUDA(cudaGetLastError());
         {
             ProfScope ps(c, PROF_REFRESH);
-            if (int rc = rates_rows_dirty(c, R.eval_lo, R.eval_hi, c->stamp, (uint32_t)(c->sweep_index + 1), c->dirty,
+            if (int rc = rates_rows_dirty(c, R.eval_lo, R.eval_hi, c->stamp, stamp_id, c->dirty,
                                           &c->sweep->n_dirty))
                 return rc;
         }
