@@ -240,7 +240,8 @@ def main():
         events = float(ev.item())
     else:
         events = float(res["events_applied"])
-    prof = {k: ctx.profile_read(k) for k in ("decide", "pick", "apply", "refresh", "thermal", "rates", "halo")}
+    KINDS = ("decide", "pick", "apply", "refresh", "thermal", "rates", "halo", "allreduce", "boundary", "step")
+    prof = {k: ctx.profile_read(k) for k in KINDS}
     value = sites_total * args.steps / (ms * 1e-3)
     peak, peak_kind = peaks()
     # planes a dense kernel processes: the owned planes plus the ghost planes it must evaluate (N > 1)
@@ -255,14 +256,27 @@ def main():
         return {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "launches": int(n),
                 "ms_per_launch": t_ms / n, "bytes_per_launch": nbytes}
 
+    def roof_rates():
+        # full rebuilds (one per thermal step) plus, for N > 1, the 6-plane ghost-zone rebuilds of every sweep
+        t_ms, n = prof["rates"]
+        n_full = prof["thermal"][1]
+        if n == 0 or t_ms <= 0:
+            return None
+        faces = 0 if world == 1 else (1 if rank in (0, world - 1) else 2)
+        nbytes = BYTES_RATES * (n_full * eval_sites + args.steps * faces * 6 * L * L)
+        ach = nbytes / (t_ms * 1e-3) / 1e9
+        return {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "launches": int(n),
+                "ms_total": t_ms, "bytes_total": nbytes}
+
     refreshed = res["sites_refreshed"] / max(args.steps, 1)
     rl = {
         "sweep_stream_kernel": roof("decide", BYTES_STREAM * eval_sites),
         "dirty_scan+dirty_eval (neighbour-rate refresh)": roof("refresh", BYTES_RATES * refreshed + BYTES_STAMP * eval_sites),
-        "rates_rows_kernel (dense rebuild after the thermal step)": roof("rates", BYTES_RATES * eval_sites),
+        "rates_rows_kernel (dense rebuild after the thermal step)": roof_rates(),
         "thermal_kernel": roof("thermal", BYTES_THERMAL * (i_end - i_begin) * L * L),
     }
-    share = {k: prof[k][0] for k in ("decide", "pick", "apply", "refresh", "thermal", "rates", "halo")}
+    share = {k: prof[k][0] for k in ("decide", "pick", "apply", "refresh", "thermal", "rates", "halo", "allreduce")}
+    share["boundary_other"] = max(prof["boundary"][0] - (prof["rates"][0] - 0.0 if world > 1 else 0.0), 0.0) if world > 1 else 0.0
     dominant = max(share, key=share.get)
     dom_name = {"decide": "sweep_stream_kernel", "refresh": "dirty_scan+dirty_eval (neighbour-rate refresh)",
                 "rates": "rates_rows_kernel (dense rebuild after the thermal step)", "thermal": "thermal_kernel"}.get(dominant)
@@ -288,6 +302,7 @@ def main():
                    "parallelism": f"zslab{world}"},
         "executed_events_per_s": events / (ms * 1e-3),
         "kernel_ms_per_step": {k: v / args.steps for k, v in share.items()},
+        "step_span_ms": prof["step"][0] / args.steps,
         "roofline": main_roof,
         "roofline_all": rl,
         # per sweep: reset, stream, plane-reduce, pick, apply, dirty-scan, dirty-eval, finalize

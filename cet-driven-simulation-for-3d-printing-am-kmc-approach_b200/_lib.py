@@ -381,7 +381,7 @@ class Context:
         check(lib().cet_sweep_reset(self._h), "cet_sweep_reset")
 
     # -- timing -----------------------------------------------------------------------------
-    PROF_KINDS = dict(decide=0, apply=1, thermal=2, rates=3, halo=4, step=5, pick=6, refresh=7)
+    PROF_KINDS = dict(decide=0, apply=1, thermal=2, rates=3, halo=4, step=5, pick=6, refresh=7, allreduce=8, boundary=9)
 
     def profile_enable(self, on=True):
         check(lib().cet_profile_enable(self._h, 1 if on else 0), "cet_profile_enable")

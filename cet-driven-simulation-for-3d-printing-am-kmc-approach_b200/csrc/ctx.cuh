@@ -146,7 +146,7 @@ int orient_update(cet_ctx *c, int64_t p_lo, int64_t p_hi);
 int nst_build(cet_ctx *c, int p_lo, int p_hi);     // rebuild the neighbour-state cache of local planes [p_lo, p_hi)
 int nst_ensure(cet_ctx *c);                          // ... of every plane it can be built for, if it is stale   // v := unit_vector(theta, phi) on local planes
 enum { PROF_DECIDE = 0, PROF_APPLY = 1, PROF_THERMAL = 2, PROF_RATES = 3, PROF_HALO = 4, PROF_STEP = 5, PROF_PICK = 6,
-       PROF_REFRESH = 7, PROF_KINDS = 8 };
+       PROF_REFRESH = 7, PROF_ALLREDUCE = 8, PROF_BOUNDARY = 9, PROF_KINDS = 10 };
 // RAII span: records an event pair around a launch when profiling is on.
 struct ProfScope {
     cet_ctx *c; int kind; cudaEvent_t a = nullptr;

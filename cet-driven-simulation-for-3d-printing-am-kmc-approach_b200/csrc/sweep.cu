@@ -578,7 +578,10 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
             c->blk_sum, c->blk_max, tpp, n_eval, i_off + R.eval_lo, (int)c->i_begin, (int)c->i_end,
             c->plane_sum, max_slot);
         CET_CUDA(cudaGetLastError());
-        if (c->world > 1) if (int rc = comm_sweep_reduce(c, c->plane_sum, (int)c->n0, max_slot)) return rc;
+        if (c->world > 1) {
+            ProfScope ps(c, PROF_ALLREDUCE);
+            if (int rc = comm_sweep_reduce(c, c->plane_sum, (int)c->n0, max_slot)) return rc;
+        }
         {
             PickArgs a;
             a.g = c->lat(); a.theta = c->theta; a.phi = c->phi; a.site_rate = c->site_rate; a.dep_rate = c->dep_rate;
@@ -617,6 +620,8 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
                 ProfScope ps(c, PROF_HALO);
                 if (int rc = comm_halo_exchange(c, 1 | 2)) return rc;
             }
+            ProfScope pb(c, PROF_BOUNDARY);
+            c->nst_valid = true;       // the exchange marked the whole cache stale; only the planes rebuilt below are
             // The ghost planes now hold the owners' lattice.  Events this slab could not resolve
             // (write set reaching beyond ghost depth 2) may have changed ghost planes that the two
             // outermost owned planes read, so the dense rebuild covers the evaluated ghost planes
@@ -629,7 +634,6 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
                 if (int rc = nst_build(c, R.own_hi - 2, R.eval_hi)) return rc;
                 if (int rc = rates_rows(c, R.own_hi - 2, R.eval_hi)) return rc;
             }
-            c->nst_valid = true;       // the exchange marked the cache stale; the two rebuilds above repaired it
         }
         c->sweep_index++;
     }

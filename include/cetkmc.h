@@ -183,7 +183,7 @@ int cet_debug_nst_mismatches(cet_ctx *ctx, int64_t *n_bad);
 /* ---- per-kernel device timing: CUDA event pairs recorded on the context stream around every
  * launch of a kind while enabled.  kind: 0 sweep stream (fire decision), 1 sweep apply,
  * 2 thermal stencil, 3 dense rate kernel, 4 halo exchange, 5 whole sweep, 6 sweep pick,
- * 7 neighbour-rate refresh. */
+ * 7 neighbour-rate refresh, 8 totals all-reduce, 9 ghost-zone cache + rate rebuild after the exchange. */
 int cet_profile_enable(cet_ctx *ctx, int on);
 int cet_profile_read(cet_ctx *ctx, int kind, double *ms_total, int64_t *launches, int reset);
 
