@@ -280,10 +280,14 @@ def main():
     dominant = max(share, key=share.get)
     dom_name = {"decide": "sweep_stream_kernel", "refresh": "dirty_scan+dirty_eval (neighbour-rate refresh)",
                 "rates": "rates_rows_kernel (dense rebuild after the thermal step)", "thermal": "thermal_kernel"}.get(dominant)
-    traffic = None
+    traffic = None                   # dram__bytes_read+write per launch from the committed ncu capture
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(dominant)
+            per = json.load(f)["per_kernel"]
+        pick_k = {"decide": ["sweep_stream_kernel"], "refresh": ["dirty_scan_kernel", "dirty_eval_kernel"],
+                  "rates": ["rates_rows_kernel"], "thermal": ["thermal_kernel_v2"]}.get(dominant, [])
+        vals = [v for k, v in per.items() if any(n in k for n in pick_k)]
+        traffic = sum(vals[:len(pick_k)]) if vals else None
     except Exception:
         pass
     main_roof = dict(rl[dom_name]) if dom_name and rl.get(dom_name) else {"achieved": None, "peak": peak, "unit": "GB/s", "frac": None}

@@ -578,10 +578,6 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
             c->blk_sum, c->blk_max, tpp, n_eval, i_off + R.eval_lo, (int)c->i_begin, (int)c->i_end,
             c->plane_sum, max_slot);
         CET_CUDA(cudaGetLastError());
-        if (c->world > 1) {
-            ProfScope ps(c, PROF_ALLREDUCE);
-            if (int rc = comm_sweep_reduce(c, c->plane_sum, (int)c->n0, max_slot)) return rc;
-        }
         {
             PickArgs a;
             a.g = c->lat(); a.theta = c->theta; a.phi = c->phi; a.site_rate = c->site_rate; a.dep_rate = c->dep_rate;
@@ -611,6 +607,12 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
             if (int rc = rates_rows_dirty(c, R.eval_lo, R.eval_hi, c->stamp, stamp_id, c->dirty,
                                           &c->sweep->n_dirty))
                 return rc;
+        }
+        // the totals are only needed for the next tau: reduce them here, next to the halo exchange, so
+        // that a sweep has one inter-rank synchronisation point instead of two
+        if (c->world > 1) {
+            ProfScope ps(c, PROF_ALLREDUCE);
+            if (int rc = comm_sweep_reduce(c, c->plane_sum, (int)c->n0, max_slot)) return rc;
         }
         sweep_finalize_kernel<<<1, 256, 0, c->stream>>>(c->sweep, c->plane_sum, (int)c->n0, max_slot,
                                                         sp->events_per_sweep, sp->p_max);
