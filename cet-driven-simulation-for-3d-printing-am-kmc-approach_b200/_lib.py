@@ -104,6 +104,9 @@ SIGNATURES = {
     "cet_comm_destroy": [_VP],
     "cet_halo_exchange": [_VP, C.c_int],
     "cet_allreduce_f64": [_VP, _VP, C.c_int, C.c_int],
+    "cet_grains_label": [_VP, _F64, C.POINTER(_I64)],
+    "cet_grains_stats": [_VP, _I64, _VP, _VP, _VP, _VP],
+    "cet_grains_download_labels": [_VP, _VP],
     "cet_debug_nst_mismatches": [_VP, C.POINTER(_I64)],
     "cet_profile_enable": [_VP, C.c_int],
     "cet_profile_read": [_VP, C.c_int, C.POINTER(_F64), C.POINTER(_I64), C.c_int],
@@ -371,6 +374,30 @@ class Context:
         v = np.ascontiguousarray(values, dtype=np.float64).copy()
         check(lib().cet_allreduce_f64(self._h, _ptr(v), v.size, op), "cet_allreduce_f64")
         return v
+
+    # -- grains (utils.get_clusters on the resident lattice) ------------------------------------
+    def grains(self, theta_threshold=0.5, labels=False):
+        """Grains of the resident lattice in the reference's cluster order (raster order of each
+        grain's first voxel, utils.py:28-84).  Returns a dict: n, root (C-order site index of the
+        first voxel), size (voxels), box_lo / box_hi (n, 3); with labels=True also `labels`, the
+        reference's `visited` volume (grain number 1.. per occupied site, 0 for empty)."""
+        n = C.c_int64(0)
+        check(lib().cet_grains_label(self._h, float(theta_threshold), C.byref(n)), "cet_grains_label")
+        n = n.value
+        root, size = np.empty(n, np.int32), np.empty(n, np.int32)
+        lo, hi = np.empty((n, 3), np.int32), np.empty((n, 3), np.int32)
+        if n:
+            check(lib().cet_grains_stats(self._h, n, _ptr(root), _ptr(size), _ptr(lo), _ptr(hi)), "cet_grains_stats")
+        order = np.argsort(root, kind="stable")
+        out = dict(n=n, root=root[order], size=size[order], box_lo=lo[order], box_hi=hi[order])
+        if labels:
+            lab = np.empty(self.owned_shape, np.int32)
+            check(lib().cet_grains_download_labels(self._h, _ptr(lab)), "cet_grains_download_labels")
+            vis = np.zeros(self.owned_shape, np.int32)
+            occ = lab >= 0
+            vis[occ] = np.searchsorted(out["root"], lab[occ]).astype(np.int32) + 1
+            out["labels"] = vis
+        return out
 
     def nst_mismatches(self):
         n = C.c_int64(0)

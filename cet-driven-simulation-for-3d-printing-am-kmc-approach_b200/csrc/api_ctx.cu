@@ -271,7 +271,8 @@ int cet_destroy(cet_ctx *c)
     void *ptrs[] = {c->vox, c->vox_prev, c->theta, c->phi, c->v, c->nst, c->T, c->T2, c->site_rate, c->dep_rate,
                     c->row_occ, c->row_emp, c->row_dep, c->row_depcnt, c->seg, c->total, c->q_top,
                     c->stage, c->kmc, c->d_py, c->d_np, c->d_sp, c->d_log, c->sweep, c->claim,
-                    c->records, c->blk_sum, c->blk_max, c->plane_sum, c->stamp, c->dirty, c->fired};
+                    c->records, c->blk_sum, c->blk_max, c->plane_sum, c->stamp, c->dirty, c->fired,
+                    c->grain_label, c->grain_gid};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &sp : c->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }

@@ -117,6 +117,10 @@ struct cet_ctx {
     double *blk_sum = nullptr, *blk_max = nullptr, *plane_sum = nullptr;
     int64_t n_blk = 0;
 
+    // grain clustering (grains.cu)
+    int *grain_label = nullptr, *grain_gid = nullptr;
+    int64_t n_grains = 0;
+
     // per-kernel-kind device timing (cet_profile_*): event pairs recorded around the dominant
     // kernels on the context stream, resolved when the totals are read
     bool profile = false;

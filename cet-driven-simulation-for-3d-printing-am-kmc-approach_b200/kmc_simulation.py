@@ -37,12 +37,17 @@ try:
     from defects import introduce_defects                 # type: ignore
 except Exception:                                         # noqa: BLE001
     introduce_defects = _host.introduce_defects
-try:
+# Observables: grains are clustered on the GPU from the resident lattice (csrc/grains.cu).
+# CETKMC_METRICS=host selects the NumPy/SciPy restatement in _host.py, CETKMC_METRICS=reference
+# the caller's own metrics.py (pure-Python DFS, utils.py:28-84).
+from . import metrics as _gpu_metrics
+_METRICS_MODE = os.environ.get("CETKMC_METRICS", "gpu")
+if _METRICS_MODE == "reference":
     from metrics import compute_metrics, detect_CET_transition   # type: ignore
-    _metrics_is_reference = True
-except Exception:                                         # noqa: BLE001
+elif _METRICS_MODE == "host":
     compute_metrics, detect_CET_transition = _host.compute_metrics, _host.detect_CET_transition
-    _metrics_is_reference = False
+else:
+    compute_metrics, detect_CET_transition = _gpu_metrics.compute_metrics, _gpu_metrics.detect_CET_transition
 
 LATTICE_SIZE = constants.LATTICE_SIZE
 N_STEPS = constants.N_STEPS
@@ -59,10 +64,13 @@ def _replay(stream_state_setter, state, draw, n):
 
 
 def _metrics_row(step, total_time, state, atom_type, theta, phi, defects_mask, nucleation_count,
-                 cet_detected, consts):
+                 cet_detected, consts, ctx=None):
     """kmc_simulation.py:341-378 — one metrics.csv row."""
     G, R, R_phys, G_over_R_phys = consts
-    m = compute_metrics(state, theta, phi, defects=defects_mask, voxel_size=constants.VOXEL_SIZE)
+    if ctx is not None and _METRICS_MODE == "gpu":
+        m = compute_metrics(state, theta, phi, defects=defects_mask, voxel_size=constants.VOXEL_SIZE, ctx=ctx)
+    else:
+        m = compute_metrics(state, theta, phi, defects=defects_mask, voxel_size=constants.VOXEL_SIZE)
     defect_voxels = int(np.sum(atom_type == constants.DEFECT_ID))
     m["Defect_voxel_count"] = defect_voxels
     m["DefectDensity"] = float(defect_voxels / atom_type.size)
@@ -184,7 +192,7 @@ def run_kmc(L: int = LATTICE_SIZE, n_steps: int = N_STEPS, temp: float = T_SUB,
                 defects_mask, _ = introduce_defects(state, atom_type, T, apply_to_state=False)
                 ctx.upload(defects=defects_mask)
             row, cet_detected = _metrics_row(last_step, total_time, state, atom_type, theta, phi,
-                                             defects_mask, nucleation_count, cet_detected, consts)
+                                             defects_mask, nucleation_count, cet_detected, consts, ctx=ctx)
             rows.append(row)
         if terminated:
             ctx.download(out=dict(state=state, atom_type=atom_type, theta=theta, phi=phi, T=T))

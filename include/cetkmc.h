@@ -176,6 +176,17 @@ int cet_comm_destroy(cet_ctx *ctx);
 int cet_halo_exchange(cet_ctx *ctx, int fields);
 int cet_allreduce_f64(cet_ctx *ctx, double *inout_host, int n, int op /* 0 sum, 1 max */);
 
+/* ---- utils.get_clusters / metrics.compute_metrics (utils.py:28-84,104-111; metrics.py:41-96) ----
+ * Grains = connected components of occupied sites (state != 0) joined by the 14-offset
+ * neighbourhood with misorientation < theta_threshold.  Whole-lattice contexts only. */
+int cet_grains_label(cet_ctx *ctx, double theta_threshold, int64_t *n_grains);
+/* Per grain (arbitrary order; sort by root for the reference's cluster order): root = smallest
+ * C-order site index (the grain's first voxel), voxel count, bounding box lo/hi [3*g + axis]. */
+int cet_grains_stats(cet_ctx *ctx, int64_t cap, int32_t *root, int32_t *size, int32_t *box_lo,
+                     int32_t *box_hi);
+/* Label volume: root site index per occupied site, -1 for empty sites. */
+int cet_grains_download_labels(cet_ctx *ctx, int32_t *labels);
+
 /* Test hook: number of sites whose cached neighbour-state word differs from a fresh gather
  * (-1 when the cache is declared stale). */
 int cet_debug_nst_mismatches(cet_ctx *ctx, int64_t *n_bad);

@@ -6,7 +6,8 @@ code on seeded inputs:
     rates_*.npz       get_event_rates (kmc_event_rates.py:162) event lists
     thermal_*.npz     update_temperature_cet / update_temperature (thermal_solver.py:36,107)
     traj_*.npz        run_kmc (kmc_simulation.py:203) final arrays + metrics.csv rows
-Usage:  python oracle/gen_golden.py
+    grains_*.npz      utils.get_clusters / metrics.compute_metrics (utils.py:69, metrics.py:41)
+Usage:  python oracle/gen_golden.py [--grains-only]
 """
 import io
 import os
@@ -47,9 +48,36 @@ def rates_case(ref, name, state, theta, phi, T, defects, impurity_c, nb_seed_val
     print(f"rates_{name}: L={L} events={len(ev)}")
 
 
+def grains_cases(ref):
+    """utils.get_clusters / metrics.compute_metrics (utils.py:69, metrics.py:41) on seeded lattices."""
+    ut, me = ref["utils"], ref["metrics"]
+    for name, L, seed, grain, fill, jitter in (("grown12", 12, 3, 4, 0.7, 0.15), ("grown16", 16, 8, 5, 0.45, 0.3),
+                                               ("half14", 14, 21, 4, None, None)):
+        if fill is None:
+            st, th, ph, _, df = O.half_grown_lattice(L, seed=seed, grain=grain)
+        else:
+            st, th, ph = O.grown_lattice(L, seed=seed, grain=grain, fill=fill, jitter=jitter)
+            df = (st == 4).astype(np.int64)
+        clusters, visited = ut.get_clusters(st, th, ph, theta_threshold=0.5)
+        m = me.compute_metrics(st, th, ph, defects=df)
+        ars = np.array([ut.calculate_aspect_ratio(c) for c in clusters])
+        keys = ("AspectRatio", "EquiaxedFraction", "NucleationDensity", "AvgGrainSize", "GrainCount", "DefectDensity",
+                "Grain_d50_um", "Grain_d90_um")
+        np.savez_compressed(os.path.join(OUT, f"grains_{name}.npz"), state=st.astype(np.int8), theta=th, phi=ph,
+                            defects=df.astype(np.int8), visited=np.asarray(visited, dtype=np.int32),
+                            sizes=np.array([len(c) for c in clusters], dtype=np.int32), aspect=ars,
+                            first=np.array([(c[0][0] * L + c[0][1]) * L + c[0][2] for c in clusters], dtype=np.int32),
+                            cet=np.array(me.compute_CET(st, th, ph)),
+                            **{f"m_{k}": np.float64(m[k]) for k in keys})
+        print(f"grains_{name}: L={L} grains={len(clusters)} AR={m['AspectRatio']:.4f} eq={m['EquiaxedFraction']:.3f}")
+
+
 def main():
     ref = refharness.load()
     os.makedirs(OUT, exist_ok=True)
+    if "--grains-only" in sys.argv:
+        grains_cases(ref)
+        return
     li, ts, km = ref["lattice_init"], ref["thermal_solver"], ref["kmc_simulation"]
 
     # ---- rates -----------------------------------------------------------------------------
@@ -91,6 +119,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "thermal_full10.npz"), T0=T0, state=st.astype(np.int8),
                         prev_state=prev.astype(np.int8), T1=Tn, T2=Tn2)
     print("thermal fixtures written")
+
+    grains_cases(ref)
 
     # ---- trajectories ------------------------------------------------------------------------
     import pandas as pd

@@ -412,3 +412,97 @@ def run_kmc(L=30, n_steps=20000, temp=2800, defect_fraction=0.0, n_seeds=5, impu
     info = dict(steps=step, terminated=terminated, nucleation_count=nuc, T=T, defects=defects,
                 logs=logs)
     return state, atom_type, total_time, theta, phi, info
+
+
+# ---------------------------------------------------------------------------
+# Grain clustering and observables (utils.py:28-84,104-111; metrics.py:41-105) — pure-Python
+# restatement for small lattices (the reference's own DFS is pure Python too).
+# ---------------------------------------------------------------------------
+_NB_OFFSETS = ((1, 1, 0), (1, -1, 0), (-1, 1, 0), (-1, -1, 0), (0, 1, 1), (0, 1, -1), (0, -1, 1), (0, -1, -1),
+               (2, 0, 0), (-2, 0, 0), (0, 2, 0), (0, -2, 0), (0, 0, 2), (0, 0, -2))   # kmc_event_rates.py:29-36
+
+
+def _py_misorientation(t1, p1, t2, p2):
+    """kmc_event_rates.py:10-23"""
+    v1 = (math.sin(t1) * math.cos(p1), math.sin(t1) * math.sin(p1), math.cos(t1))
+    v2 = (math.sin(t2) * math.cos(p2), math.sin(t2) * math.sin(p2), math.cos(t2))
+    dot = v1[0] * v2[0] + v1[1] * v2[1] + v1[2] * v2[2]
+    return math.acos(max(min(dot, 1.0), -1.0))
+
+
+def get_clusters(state, theta, phi=None, theta_threshold=0.5):
+    """utils.py:28-84: DFS over the 14-neighbourhood; clusters in discovery (raster) order, each
+    a list of (i, j, k) in DFS order; `visited` holds the cluster number 1.. per site."""
+    Lx, Ly, Lz = state.shape
+    visited = np.zeros(state.shape, dtype=np.int32)
+    occ = (state != 0).tolist()
+    th = theta.tolist()
+    ph = phi.tolist() if phi is not None else None
+    vis = visited.tolist()
+    clusters, label = [], 1
+    for i in range(Lx):
+        for j in range(Ly):
+            for k in range(Lz):
+                if not occ[i][j][k] or vis[i][j][k]:
+                    continue
+                cluster, stack = [(i, j, k)], [(i, j, k)]
+                vis[i][j][k] = label
+                while stack:
+                    ci, cj, ck = stack.pop()
+                    for di, dj, dk in _NB_OFFSETS:
+                        ni, nj, nk = ci + di, cj + dj, ck + dk
+                        # get_bcc_neighbors bounds every axis by Lx (utils.py:46), then :49 by the true extents
+                        if not (0 <= ni < Lx and 0 <= nj < Lx and 0 <= nk < Lx):
+                            continue
+                        if not (nj < Ly and nk < Lz) or not occ[ni][nj][nk] or vis[ni][nj][nk]:
+                            continue
+                        if ph is None:
+                            mis = abs(th[ci][cj][ck] - th[ni][nj][nk])
+                        else:
+                            mis = _py_misorientation(th[ci][cj][ck], ph[ci][cj][ck], th[ni][nj][nk], ph[ni][nj][nk])
+                        if mis < theta_threshold:
+                            vis[ni][nj][nk] = label
+                            cluster.append((ni, nj, nk))
+                            stack.append((ni, nj, nk))
+                clusters.append(cluster)
+                label += 1
+    return clusters, np.array(vis, dtype=np.int32).reshape(state.shape)
+
+
+def calculate_aspect_ratio(cluster):
+    """utils.py:104-111"""
+    c = np.array(cluster)
+    dims = c.max(axis=0) - c.min(axis=0) + 1
+    return float(np.max(dims)) / float(max(np.min(dims), 1))
+
+
+def compute_metrics(state, theta, phi, defects=None, voxel_size=None):
+    """metrics.py:41-96, the keys the driver consumes (kmc_simulation.py:341-378)."""
+    voxel_size = CONSTANTS["VOXEL_SIZE"] if voxel_size is None else voxel_size
+    clusters, visited = get_clusters(state, theta, phi, 0.5)
+    if not clusters:
+        return {"AspectRatio": 0.0, "EquiaxedFraction": 0.0, "NucleationDensity": 0.0, "AvgGrainSize": 0.0,
+                "GrainCount": 0, "DefectDensity": 0.0, "Grain_d50_um": 0.0, "Grain_d90_um": 0.0}
+    ars = [calculate_aspect_ratio(c) for c in clusters]
+    volume = state.size * (voxel_size ** 3)
+    def_count = np.sum(defects) if defects is not None else 0
+    diam = ((6.0 * (np.array(visited) * (voxel_size ** 3)) / np.pi) ** (1.0 / 3.0)) * 1e6   # metrics.py:43,76
+    return {"AspectRatio": np.mean(ars), "EquiaxedFraction": np.mean(np.array(ars) < CONSTANTS["CET_AR_THRESHOLD"]),
+            "NucleationDensity": len(clusters) / volume, "AvgGrainSize": np.mean([len(c) for c in clusters]) * voxel_size * 1e6,
+            "GrainCount": len(clusters), "DefectDensity": def_count / volume,
+            "Grain_d50_um": np.median(diam), "Grain_d90_um": np.percentile(diam, 90)}
+
+
+def grown_lattice(L, seed=1, grain=5, fill=0.7, jitter=0.15):
+    """Clustering input: `fill` of the sites occupied, piecewise-constant grain orientations of
+    edge `grain` with a per-site orientation jitter (rad), so that edges fall on both sides of
+    the 0.5 rad threshold; 2 % defect sites (state 4, theta = phi = 0)."""
+    rng = np.random.default_rng(seed)
+    g = (L + grain - 1) // grain
+    up = lambda a: np.repeat(np.repeat(np.repeat(a, grain, 0), grain, 1), grain, 2)[:L, :L, :L]
+    th = up(rng.uniform(0, np.pi, (g, g, g))) + jitter * rng.standard_normal((L, L, L))
+    ph = up(rng.uniform(0, 2 * np.pi, (g, g, g))) + jitter * rng.standard_normal((L, L, L))
+    state = np.where(rng.random((L, L, L)) < fill, rng.choice(np.array([1, 2, 3]), size=(L, L, L), p=[.8, .15, .05]), 0)
+    state = np.where((state != 0) & (rng.random((L, L, L)) < 0.02), 4, state).astype(np.int64)
+    solid = (state >= 1) & (state <= 3)
+    return state, np.ascontiguousarray(np.where(solid, th, 0.0)), np.ascontiguousarray(np.where(solid, ph, 0.0))

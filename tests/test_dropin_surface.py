@@ -60,7 +60,8 @@ sys.modules["mpl_toolkits.mplot3d"].Axes3D = object
 import kmc_simulation, kmc_event_rates, thermal_solver, utils, metrics
 assert kmc_simulation.run_kmc.__module__ == "cetkmc.kmc_simulation"
 assert kmc_simulation.initialize_lattice.__module__ == "lattice_init"
-assert kmc_simulation.compute_metrics.__module__ == "metrics"
+assert kmc_simulation.compute_metrics.__module__ == "cetkmc.metrics"
+assert metrics.compute_CET.__module__ == "cetkmc.metrics" and metrics.detect_CET_transition.__module__ == "cetkmc.metrics"
 assert utils.get_bcc_neighbors.__module__ == "cetkmc.kmc_event_rates"
 assert thermal_solver.update_temperature_cet.__module__ == "cetkmc.thermal_solver"
 from cetkmc._config import constants

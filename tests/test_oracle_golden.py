@@ -74,3 +74,18 @@ def test_neighbors_and_misorientation(oracle):
     assert oracle.bcc_neighbors(0, 0, 0, 1).shape == (0, 3)
     assert oracle.misorientation(0.3, 1.0, 0.3, 1.0) < 1e-7
     assert abs(oracle.misorientation(0.0, 0.0, np.pi / 2, 0.0) - np.pi / 2) < 1e-15
+
+
+@pytest.mark.parametrize("name", ["grains_grown12.npz", "grains_grown16.npz", "grains_half14.npz"])
+def test_grain_clustering_golden(oracle, name):
+    """utils.get_clusters / metrics.compute_metrics restatement against the reference's output."""
+    g = golden(name)
+    st, th, ph = g["state"].astype(np.int64), g["theta"], g["phi"]
+    clusters, visited = oracle.get_clusters(st, th, ph, 0.5)
+    np.testing.assert_array_equal(visited, g["visited"])
+    np.testing.assert_array_equal([len(c) for c in clusters], g["sizes"])
+    np.testing.assert_array_equal([oracle.calculate_aspect_ratio(c) for c in clusters], g["aspect"])
+    m = oracle.compute_metrics(st, th, ph, defects=g["defects"].astype(np.int64))
+    for k in ("AspectRatio", "EquiaxedFraction", "NucleationDensity", "AvgGrainSize", "GrainCount", "DefectDensity",
+              "Grain_d50_um", "Grain_d90_um"):
+        assert m[k] == g[f"m_{k}"], k
