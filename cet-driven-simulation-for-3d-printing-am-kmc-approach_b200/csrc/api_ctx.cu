@@ -3,6 +3,7 @@
 // lattice_init.py:23-32) and the packed HBM layout (1 byte per voxel + float64 fields).
 #include <stdarg.h>
 #include "ctx.cuh"
+#include "rate_tile.cuh"
 
 namespace cet {
 
@@ -73,40 +74,28 @@ __global__ void orient_kernel(const double *__restrict__ theta, const double *__
         v[q] = unit_vec4(theta[q], phi[q]);
 }
 
-// nst[s] = packed states of the 14 neighbours of s (0 for neighbours outside the global lattice)
-__global__ void nst_build_kernel(const uint8_t *__restrict__ vox, uint64_t *nst, int L, int n0, int i_off, int p_lo,
-                                 int p_hi)
+// nst[s] = cached neighbour-state word of s (rate_tile.cuh: nst_word)
+__global__ void nst_build_kernel(const uint64_t lut, const uint8_t *__restrict__ vox, uint64_t *nst, int L, int n0,
+                                 int i_off, int p_lo, int p_hi)
 {
     const int64_t LL = (int64_t)L * L;
     const int64_t n = (int64_t)(p_hi - p_lo) * LL;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
         const int64_t s = (int64_t)p_lo * LL + q;
         const int p = (int)(s / LL), j = (int)((s / L) % L), k = (int)(s % L);
-        const unsigned inb = inbounds_mask(i_off + p, j, k, n0, L);
-        uint64_t w = 0;
-#pragma unroll
-        for (int o = 0; o < 14; ++o)
-            if (inb >> o & 1u)
-                w |= (uint64_t)(vox[s + ((int64_t)CET_NB_DI(o) * L + CET_NB_DJ(o)) * L + CET_NB_DK(o)] & 15) << (4 * o);
-        nst[s] = w;
+        nst[s] = nst_word(lut, vox, s, i_off + p, j, k, n0, L);
     }
 }
 
-__global__ void nst_check_kernel(const uint8_t *__restrict__ vox, const uint64_t *__restrict__ nst, int L, int n0,
-                                 int i_off, int p_lo, int p_hi, unsigned long long *bad)
+__global__ void nst_check_kernel(const uint64_t lut, const uint8_t *__restrict__ vox, const uint64_t *__restrict__ nst,
+                                 int L, int n0, int i_off, int p_lo, int p_hi, unsigned long long *bad)
 {
     const int64_t LL = (int64_t)L * L;
     const int64_t n = (int64_t)(p_hi - p_lo) * LL;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
         const int64_t s = (int64_t)p_lo * LL + q;
         const int p = (int)(s / LL), j = (int)((s / L) % L), k = (int)(s % L);
-        const unsigned inb = inbounds_mask(i_off + p, j, k, n0, L);
-        uint64_t w = 0;
-#pragma unroll
-        for (int o = 0; o < 14; ++o)
-            if (inb >> o & 1u)
-                w |= (uint64_t)(vox[s + ((int64_t)CET_NB_DI(o) * L + CET_NB_DJ(o)) * L + CET_NB_DK(o)] & 15) << (4 * o);
-        if (nst[s] != w) atomicAdd(bad, 1ull);
+        if (nst[s] != nst_word(lut, vox, s, i_off + p, j, k, n0, L)) atomicAdd(bad, 1ull);
     }
 }
 
@@ -121,7 +110,7 @@ int nst_build(cet_ctx *c, int p_lo, int p_hi)
 {
     if (p_hi <= p_lo) return 0;
     const int64_t n = (int64_t)(p_hi - p_lo) * c->plane;
-    nst_build_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->vox, c->nst, (int)c->n1, (int)c->n0,
+    nst_build_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(nb_code_lut(c->rp), c->vox, c->nst, (int)c->n1, (int)c->n0,
                                                                (int)(c->i_begin - c->halo), p_lo, p_hi);
     CET_CUDA(cudaGetLastError());
     return 0;
@@ -272,7 +261,7 @@ int cet_destroy(cet_ctx *c)
                     c->row_occ, c->row_emp, c->row_dep, c->row_depcnt, c->seg, c->total, c->q_top,
                     c->stage, c->kmc, c->d_py, c->d_np, c->d_sp, c->d_log, c->sweep, c->claim,
                     c->records, c->blk_sum, c->blk_max, c->plane_sum, c->stamp, c->dirty, c->fired,
-                    c->grain_label, c->grain_gid};
+                    c->grain_label, c->grain_gid, c->rate_tab};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &sp : c->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -298,8 +287,13 @@ int cet_set_rate_params(cet_ctx *c, const cet_rate_params *p)
     CET_REQUIRE(p->states_w >= 1 && p->states_w <= 15 && p->states_re >= 1 && p->states_re <= 15 &&
                     p->states_c >= 1 && p->states_c <= 15,
                 "cet_set_rate_params: species ids must be in 1..15");
+    CET_REQUIRE(p->states_w != p->states_re && p->states_w != p->states_c && p->states_re != p->states_c &&
+                    p->defect_id != p->states_w && p->defect_id != p->states_re && p->defect_id != p->states_c,
+                "cet_set_rate_params: the W / Re / C / defect state ids must be distinct");
     c->rp = *p;
     c->have_rp = true;
+    c->rate_tab_valid = false;
+    c->nst_valid = false;             // the cached neighbour classes depend on the state ids
     c->rates_valid = false; c->sweep_rates_valid = false;
     return 0;
 }
@@ -467,7 +461,7 @@ int cet_debug_nst_mismatches(cet_ctx *c, int64_t *n_bad)
     if (int rc = ensure_stage(c, 8)) return rc;
     CET_CUDA(cudaMemsetAsync(c->stage, 0, 8, c->stream));
     const int64_t n = (int64_t)(hi - lo) * c->plane;
-    nst_check_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->vox, c->nst, (int)c->n1, (int)c->n0, i_off, lo, hi,
+    nst_check_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(nb_code_lut(c->rp), c->vox, c->nst, (int)c->n1, (int)c->n0, i_off, lo, hi,
                                                                (unsigned long long *)c->stage);
     CET_CUDA(cudaGetLastError());
     unsigned long long h = 0;

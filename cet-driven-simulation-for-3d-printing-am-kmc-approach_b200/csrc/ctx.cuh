@@ -94,8 +94,10 @@ struct cet_ctx {
     void *stage = nullptr;
     size_t stage_bytes = 0;
 
-    cet_rate_params rp;
+    cet_rate_params rp{};
     bool have_rp = false;
+    double *rate_tab = nullptr;       // K_eff / E_tot tables of rate_tile.cuh
+    bool rate_tab_valid = false, rate_attr_set = false;
 
     // exact KMC
     cet::KmcState *kmc = nullptr;

@@ -13,116 +13,141 @@
 //   seg[3p+{0,1,2}]         : warp_strided_sum over j
 //   total                   : block_sum over seg
 //
-// Dense kernel shape: one warp per (plane, j) row — see dense_pass.cuh.
+// Dense kernel shape: one CTA per 256 consecutive sites — see rate_tile.cuh.
 #include "ctx.cuh"
-#include "dense_pass.cuh"
+#include "rate_tile.cuh"
+#include <algorithm>
+#include <stdlib.h>
 #include "reduce.cuh"
 
 namespace cet {
 
 constexpr int RB_WARPS = 8;
 
-struct RatesArgs {
-    Lat g;
-    cet_rate_params P;
-    double *site_rate, *dep_rate, *row_occ, *row_emp, *row_dep;
-    int32_t *row_depcnt;
-    int p_lo, p_hi;   // local planes to evaluate
-    const uint32_t *stamp;   // DIRTY mode: only sites with stamp == stamp_id are re-evaluated
-    uint32_t stamp_id;
-};
-
-// dynamic shared memory per warp: rate_row[L] doubles, then the two uint16 index lists
-__host__ __device__ inline size_t dense_smem_per_warp(int L, bool with_rates)
+// K_eff / E_tot tables of rate_tile.cuh, from the per-event inline functions themselves.
+__global__ void rate_tables_kernel(const cet_rate_params P, double *tab)
 {
-    const size_t lists = (((size_t)2 * L * sizeof(uint16_t)) + 15) & ~(size_t)15;
-    return lists + (with_rates ? (size_t)L * sizeof(double) : 0);
+    const int t = threadIdx.x;
+    if (t < 256) tab[RT_KEFF + t] = nuc_K_eff(P, t >> 4, t & 15);
+    if (t < 48) tab[RT_ETOT + t] = occ_E_tot(P, t >> 4, t & 15);
+    if (t < 32) tab[RT_EXP2 + t] = d_exp2_tab[t];
+    if (t < 4) tab[RT_HE + t] = 0.5 * P.E_b[t == 3 ? 1 : t];
 }
 
-__global__ void __launch_bounds__(RB_WARPS * 32) rates_rows_kernel(const RatesArgs a)
+struct RateTileArgs;
+template <int MINB>
+__global__ void rates_tile_kernel(const __grid_constant__ RateTileArgs a, int s_lo, int s_hi, unsigned int *queue);
+__global__ void dirty_eval_kernel(const __grid_constant__ RateTileArgs a, const int32_t *list, const unsigned int *n_list,
+                                  unsigned int *queue);
+
+static int rate_tables_ensure(cet_ctx *c)
 {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    __shared__ NbOffsets nbt;
-    const int L = a.g.L;
-    nb_offsets_init(&nbt, L);
+    if (!c->rate_attr_set) {                 // per device; a context lives on one device
+        CET_CUDA(cudaFuncSetAttribute(rates_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
+        CET_CUDA(cudaFuncSetAttribute(rates_tile_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
+        CET_CUDA(cudaFuncSetAttribute(rates_tile_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
+        CET_CUDA(cudaFuncSetAttribute(dirty_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
+        c->rate_attr_set = true;
+    }
+    if (c->rate_tab_valid) return 0;
+    if (!c->rate_tab) CET_CUDA(cudaMalloc(&c->rate_tab, RT_TABLE_DOUBLES * sizeof(double) + 64));
+    rate_tables_kernel<<<1, 256, 0, c->stream>>>(c->rp, c->rate_tab);
+    CET_CUDA(cudaGetLastError());
+    c->rate_tab_valid = true;
+    return 0;
+}
+
+static RateTileArgs tile_args(cet_ctx *c)
+{
+    RateTileArgs a;
+    a.g = c->lat();
+    a.P = c->rp;
+    a.tab = c->rate_tab;
+    a.site_rate = c->site_rate; a.dep_rate = c->dep_rate; a.nst_out = c->nst;
+    const int64_t top = c->n0 - 1 - (c->i_begin - c->halo);          // local plane of the global top
+    if (top >= 0 && top < c->np) { a.top_lo = (int)(top * c->plane); a.top_hi = (int)((top + 1) * c->plane); }
+    else { a.top_lo = 0; a.top_hi = 0; }
+    a.nloc = (int)c->nloc;
+    a.lut = nb_code_lut(c->rp);
+    return a;
+}
+
+// Dense rate kernel: persistent CTAs, warps pull 256-site chunks of [s_lo, s_hi) from the queue.
+template <int MINB>
+__global__ void __launch_bounds__(RT_THREADS, MINB) rates_tile_kernel(const __grid_constant__ RateTileArgs a, int s_lo, int s_hi,
+                                                                      unsigned int *queue)
+{
+    extern __shared__ __align__(16) unsigned char rate_dyn_smem[];
+    RateSmem &sm = *reinterpret_cast<RateSmem *>(rate_dyn_smem);
+    rate_smem_init(sm, a);
+    rate_cta_loop<false>(a, sm, s_lo, s_hi - s_lo, nullptr, queue);
+}
+
+// BKL hierarchy level 1 (exact mode only): per-row sums split by occupancy class, one warp per row.
+struct RowSumArgs {
+    const uint8_t *vox;
+    const double *site_rate, *dep_rate;
+    double *row_occ, *row_emp, *row_dep;
+    int32_t *row_depcnt;
+    int L, p_lo, p_hi, top_plane;     // top_plane: local plane of the global top or -1
+};
+__global__ void __launch_bounds__(RB_WARPS * 32) row_sums_kernel(const RowSumArgs a)
+{
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int row = blockIdx.x * RB_WARPS + wid;
-    const int nrows = (a.p_hi - a.p_lo) * L;
-    if (row >= nrows) return;
-    const int p = a.p_lo + row / L, j = row % L;
-    const int i = a.g.i_off + p;
-    const int rbase = (p * L + j) * L;
-    unsigned char *mine = dyn_smem + wid * dense_smem_per_warp(L, true);
-    double *rate_row = (double *)mine;
-    RowLists w;
-    w.occ = (uint16_t *)(mine + (size_t)L * sizeof(double));
-    w.emp = w.occ + L;
-    const bool top = i == a.g.n0 - 1;
-    if (top)
-        for (int k = lane; k < L; k += 32) a.dep_rate[j * L + k] = NAN;    // empty sites overwrite below
-    row_classify(a.g, a.P, rbase, w, rate_row, nullptr, 0u, [](int, int) {});
-    row_occupied(a.g, a.P, &nbt, i, j, rbase, w, [&](int k, double sum, bool active) {
-        if (active) rate_row[k] = sum;
-    });
-    row_empty(a.g, a.P, &nbt, i, j, rbase, w, [&](int k, double sum, bool has_dep, double dep, bool active) {
-        if (active) {
-            rate_row[k] = sum;
-            if (has_dep) a.dep_rate[j * L + k] = dep;
-        }
-    });
-    __syncwarp();
-    for (int k = lane; k < L; k += 32) a.site_rate[rbase + k] = rate_row[k];
+    if (row >= (a.p_hi - a.p_lo) * a.L) return;
+    const int p = a.p_lo + row / a.L, j = row % a.L;
+    const int64_t rbase = ((int64_t)p * a.L + j) * a.L;
     double occ, emp;
-    warp_row_sums(a.g.vox + rbase, rate_row, L, &occ, &emp);
-    if (lane == 0) { a.row_occ[p * L + j] = occ; a.row_emp[p * L + j] = emp; }
-    if (top) {
+    warp_row_sums(a.vox + rbase, a.site_rate + rbase, a.L, &occ, &emp);
+    if (lane == 0) { a.row_occ[p * a.L + j] = occ; a.row_emp[p * a.L + j] = emp; }
+    if (p == a.top_plane) {
         double ds; int dc;
-        warp_dep_row(a.dep_rate + j * L, L, &ds, &dc);
+        warp_dep_row(a.dep_rate + j * a.L, a.L, &ds, &dc);
         if (lane == 0) { a.row_dep[j] = ds; a.row_depcnt[j] = dc; }
     }
 }
 
 // Neighbour-rate refresh (sweep.cu): the sites stamped in this sweep are re-evaluated with the same
-// chunk arithmetic as the dense pass.  Two kernels:
-//   scan  streams the stamp array (4 B/site), compacts the stamped sites of each class into two
-//         global lists (one atomic per class per 8-row tile, so a list stays in lattice order and a
-//         chunk of 32 entries touches a handful of adjacent rows), and settles the sites that own
-//         no list entry (defects; occupied sites of the top plane lose their deposition event);
-//   eval  evaluates the lists 32 sites per warp with every warp of the GPU busy.
+// tile code as the dense pass.  Two kernels:
+//   scan  streams the stamp array (1 B/site) and compacts the stamped sites into one global list
+//         (one atomic per 8-row CTA, so the list stays roughly in lattice order: a tile of 32
+//         entries comes from one or two adjacent rows and its neighbour gathers coalesce;
+//         emitting the list in 8 x 8 x L blocks instead was measured and is slower, 1.43 vs 1.39 ms
+//         at 0.5 % N events per sweep and 6.2 vs 3.2 ms at 2 % N);
+//   eval  evaluates the list with the tile code of the dense pass; the cached neighbour-class
+//         word of every evaluated site is rewritten from a fresh gather (exactly the sites whose
+//         neighbourhood changed), so the apply kernel needs no atomics to maintain the cache.
 // Results go straight to site_rate / dep_rate; the BKL row sums are not maintained.
 struct DirtyArgs {
-    Lat g;
-    cet_rate_params P;
-    double *site_rate, *dep_rate;
-    uint64_t *nst;                    // cache entries of the refreshed sites are rewritten
     const uint8_t *stamp;
     uint32_t stamp_id;
-    int p_lo, p_hi;
-    int32_t *list_occ, *list_emp;     // capacity: one entry per local site
-    unsigned int *n_occ, *n_emp;      // list lengths (device counters)
+    int L, p_lo, p_hi;
+    int32_t *list;                    // capacity: one entry per local site
+    unsigned int *n_list;             // list length (device counter)
 };
+
+constexpr int DS_STAGE = 2048;     // staged list entries per CTA (8 rows)
 
 __global__ void __launch_bounds__(RB_WARPS * 32) dirty_scan_kernel(const __grid_constant__ DirtyArgs a)
 {
-    __shared__ int s_occ[RB_WARPS * 64], s_emp[RB_WARPS * 64];     // staging; spills are appended directly
-    __shared__ unsigned int c_occ, c_emp, b_occ, b_emp;
-    const int L = a.g.L;
-    if (threadIdx.x == 0) { c_occ = 0; c_emp = 0; }
+    __shared__ int s_list[DS_STAGE];                                // staging; spills are appended directly
+    __shared__ unsigned int c_list, b_list, s_first_spill;
+    const int L = a.L;
+    if (threadIdx.x == 0) { c_list = 0; s_first_spill = 0xffffffffu; }
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int nrows = (a.p_hi - a.p_lo) * L;
-    const int row = blockIdx.x * RB_WARPS + wid;
-    if (row < nrows) {
-        const int p = a.p_lo + row / L, j = row % L;
-        const bool top = a.g.i_off + p == a.g.n0 - 1;
-        const int rbase = (p * L + j) * L;
-        const bool vec = (L % 16) == 0;                      // rows are then 16-byte aligned in the stamp array
-        const uint8_t want = (uint8_t)a.stamp_id;
+    const int row = blockIdx.x * RB_WARPS + wid;             // one row per warp, 8 consecutive rows per CTA
+    const bool vec = (L % 16) == 0;                          // rows are then 16-byte aligned in the stamp array
+    const uint8_t want = (uint8_t)a.stamp_id;
+    if (row < (a.p_hi - a.p_lo) * L) {
+        const int rbase = (a.p_lo * L + row) * L;
         for (int k0 = 0; k0 < L; k0 += 512) {
             const int kb = k0 + 16 * lane;                   // this lane's sixteen consecutive sites
-            if (kb >= L) continue;
             uint32_t wv[4];
-            if (vec) {
+            if (kb >= L) {
+                wv[0] = wv[1] = wv[2] = wv[3] = 0x01010101u * (uint8_t)~want;
+            } else if (vec) {
                 const uint4 v4 = *reinterpret_cast<const uint4 *>(a.stamp + rbase + kb);
                 wv[0] = v4.x; wv[1] = v4.y; wv[2] = v4.z; wv[3] = v4.w;
             } else {
@@ -143,73 +168,52 @@ __global__ void __launch_bounds__(RB_WARPS * 32) dirty_scan_kernel(const __grid_
                 const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 in every zero byte
                 match |= (((z >> 7) & 1u) | ((z >> 14) & 2u) | ((z >> 21) & 4u) | ((z >> 28) & 8u)) << (4 * q);
             }
-            while (match) {
-            const int e = __ffs(match) - 1;
-            match &= match - 1;
-            const int k = kb + e;
-            const int st = vox_state(a.g.vox[rbase + k]);
-            if (st != 0) {
-                if (top) a.dep_rate[j * L + k] = NAN;                   // occupied: no deposition event
-                if (st == a.P.defect_id) {                               // defect: no events; repair its cache word here
-                    a.site_rate[rbase + k] = 0.0;
-                    const unsigned inb = inbounds_mask(a.g.i_off + p, j, k, a.g.n0, L);
-                    a.nst[rbase + k] = neighbour_states(a.g, rbase + k, inb);
-                    continue;
-                }
-                const unsigned int q = atomicAdd(&c_occ, 1u);
-                if (q < RB_WARPS * 64) s_occ[q] = rbase + k;
-                else a.list_occ[atomicAdd(a.n_occ, 1u)] = rbase + k;
-            } else {
-                const unsigned int q = atomicAdd(&c_emp, 1u);
-                if (q < RB_WARPS * 64) s_emp[q] = rbase + k;
-                else a.list_emp[atomicAdd(a.n_emp, 1u)] = rbase + k;
+            // k-ordered compaction of the row: warp scan of the match counts, one counter update per warp
+            const int nm = __popc(match);
+            int inc = nm;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
             }
+            const int tot = __shfl_sync(0xffffffffu, inc, 31);
+            if (tot == 0) continue;
+            unsigned int q0 = 0;
+            int spill = 0;
+            if (lane == 0) {
+                q0 = atomicAdd(&c_list, (unsigned)tot);
+                if (q0 + tot > DS_STAGE) {                                  // staging full: append directly
+                    atomicMin(&s_first_spill, q0);
+                    q0 = atomicAdd(a.n_list, (unsigned)tot);
+                    spill = 1;
+                }
+            }
+            q0 = __shfl_sync(0xffffffffu, q0, 0);
+            spill = __shfl_sync(0xffffffffu, spill, 0);
+            int *dst = (spill ? a.list : s_list) + q0 + (inc - nm);
+            while (match) {
+                const int e = __ffs(match) - 1;
+                match &= match - 1;
+                *dst++ = rbase + kb + e;
             }
         }
     }
     __syncthreads();
-    const unsigned int no = min(c_occ, (unsigned)(RB_WARPS * 64)), ne = min(c_emp, (unsigned)(RB_WARPS * 64));
-    if (threadIdx.x == 0) {
-        b_occ = no ? atomicAdd(a.n_occ, no) : 0u;
-        b_emp = ne ? atomicAdd(a.n_emp, ne) : 0u;
-    }
+    // the staged prefix is contiguous up to the first group that did not fit (its counter value q0
+    // satisfies q0 <= DS_STAGE < q0 + nm): entries [0, q0) are staged, q0 = the smallest such start
+    const unsigned int n = min(c_list, s_first_spill);
+    if (threadIdx.x == 0) b_list = n ? atomicAdd(a.n_list, n) : 0u;
     __syncthreads();
-    for (unsigned int q = threadIdx.x; q < no; q += RB_WARPS * 32) a.list_occ[b_occ + q] = s_occ[q];
-    for (unsigned int q = threadIdx.x; q < ne; q += RB_WARPS * 32) a.list_emp[b_emp + q] = s_emp[q];
+    for (unsigned int q = threadIdx.x; q < n; q += RB_WARPS * 32) a.list[b_list + q] = s_list[q];
 }
 
-__global__ void __launch_bounds__(RB_WARPS * 32) dirty_eval_kernel(const __grid_constant__ DirtyArgs a)
+__global__ void __launch_bounds__(RT_THREADS, 5) dirty_eval_kernel(const __grid_constant__ RateTileArgs a, const int32_t *list,
+                                                                   const unsigned int *n_list, unsigned int *queue)
 {
-    __shared__ NbOffsets nbt;
-    const int L = a.g.L, LL = L * L;
-    nb_offsets_init(&nbt, L);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int no = (int)*a.n_occ, ne = (int)*a.n_emp;
-    // blocked distribution: a CTA owns a contiguous run of each list (lists are in lattice order, so
-    // its warps work on adjacent rows and share neighbour rows through L1)
-    const int per_o = ((no + 31) / 32 + gridDim.x - 1) / gridDim.x * 32, per_e = ((ne + 31) / 32 + gridDim.x - 1) / gridDim.x * 32;
-    const int o_lo = blockIdx.x * per_o, o_hi = min(no, o_lo + per_o);
-    const int e_lo = blockIdx.x * per_e, e_hi = min(ne, e_lo + per_e);
-    for (int c0 = o_lo + wid * 32; c0 < o_hi; c0 += RB_WARPS * 32) {
-        const bool active = c0 + lane < o_hi;
-        const int s = a.list_occ[active ? c0 + lane : c0];
-        const int p = s / LL, j = (s / L) % L, k = s % L;
-        const double sum = occ_chunk<true>(a.g, a.P, &nbt, a.g.i_off + p, j, k, s, active, a.nst);
-        if (active) a.site_rate[s] = sum;
-    }
-    for (int c0 = e_lo + wid * 32; c0 < e_hi; c0 += RB_WARPS * 32) {
-        const bool active = c0 + lane < e_hi;
-        const int s = a.list_emp[active ? c0 + lane : c0];
-        const int p = s / LL, j = (s / L) % L, k = s % L;
-        const int i = a.g.i_off + p;
-        bool has_dep;
-        double dep;
-        const double sum = emp_chunk<true>(a.g, a.P, &nbt, i, j, k, s, active, &has_dep, &dep, a.nst);
-        if (active) {
-            a.site_rate[s] = sum;
-            if (i == a.g.n0 - 1) a.dep_rate[j * L + k] = has_dep ? dep : NAN;
-        }
-    }
+    extern __shared__ __align__(16) unsigned char rate_dyn_smem[];
+    RateSmem &sm = *reinterpret_cast<RateSmem *>(rate_dyn_smem);
+    rate_smem_init(sm, a);
+    rate_cta_loop<true>(a, sm, 0, (int)*n_list, list, queue);
 }
 
 // One warp per local plane: plane-segment sums in list order.
@@ -234,52 +238,51 @@ __global__ void total_kernel(const double *seg, const int32_t *row_depcnt, doubl
     if (threadIdx.x == 0) { total[0] = t; ((long long *)total)[1] = nd; }
 }
 
-// Dense evaluation of local planes [p_lo, p_hi): site_rate, dep_rate and the row sums.
+// Dense evaluation of local planes [p_lo, p_hi): site_rate and (on the global top plane) dep_rate.
 int rates_rows(cet_ctx *c, int p_lo, int p_hi)
 {
     CET_REQUIRE(c->cubic, "rates: context was created with cet_create_shape (thermal only)");
     CET_REQUIRE(c->have_rp, "rates: cet_set_rate_params has not been called");
     if (p_hi <= p_lo) return 0;
-    if (int rc = nst_ensure(c)) return rc;
-    RatesArgs a;
-    a.g = c->lat();
-    a.P = c->rp;
-    a.site_rate = c->site_rate; a.dep_rate = c->dep_rate;
-    a.row_occ = c->row_occ; a.row_emp = c->row_emp; a.row_dep = c->row_dep; a.row_depcnt = c->row_depcnt;
-    a.p_lo = p_lo; a.p_hi = p_hi; a.stamp = nullptr; a.stamp_id = 0;
-    const int nrows = (a.p_hi - a.p_lo) * (int)c->n1;
-    CET_REQUIRE(c->n1 <= 65535, "rates: L must fit 16-bit row indices");
     CET_REQUIRE(c->nloc < (1ll << 31), "rates: the local lattice must have fewer than 2^31 sites");
-    const size_t smem = RB_WARPS * dense_smem_per_warp((int)c->n1, true);
-    CET_REQUIRE(smem <= 220 * 1024, "rates: L=%lld needs %zu B of shared memory per CTA", (long long)c->n1, smem);
-    if (smem > 40 * 1024)
-        CET_CUDA(cudaFuncSetAttribute(rates_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = nst_ensure(c)) return rc;
+    if (int rc = rate_tables_ensure(c)) return rc;
+    const RateTileArgs a = tile_args(c);
+    const int s_lo = (int)(p_lo * c->plane), s_hi = (int)(p_hi * c->plane);
     {
         ProfScope ps(c, PROF_RATES);
-        rates_rows_kernel<<<(nrows + RB_WARPS - 1) / RB_WARPS, RB_WARPS * 32, smem, c->stream>>>(a);
+        unsigned int *queue = (unsigned int *)(c->rate_tab + RT_TABLE_DOUBLES);
+        CET_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned int), c->stream));
+        const int grid = (int)std::min<int64_t>(((int64_t)s_hi - s_lo + RT_CHUNK * RT_WARPS - 1) / (RT_CHUNK * RT_WARPS), 148 * 5);
+        static const int variant = getenv("CET_RT_MINB") ? atoi(getenv("CET_RT_MINB")) : 5;     // tuning knob (profiles/)
+        const int g6 = (int)std::min<int64_t>(((int64_t)s_hi - s_lo + RT_CHUNK * RT_WARPS - 1) / (RT_CHUNK * RT_WARPS), 148 * 6);
+        if (variant == 4) rates_tile_kernel<4><<<std::min(grid, 148 * 4), RT_THREADS, sizeof(RateSmem), c->stream>>>(a, s_lo, s_hi, queue);
+        else if (variant == 6) rates_tile_kernel<6><<<g6, RT_THREADS, sizeof(RateSmem), c->stream>>>(a, s_lo, s_hi, queue);
+        else rates_tile_kernel<5><<<grid, RT_THREADS, sizeof(RateSmem), c->stream>>>(a, s_lo, s_hi, queue);
     }
     CET_CUDA(cudaGetLastError());
     return 0;
 }
 
 // Re-evaluate, on local planes [p_lo, p_hi), the sites whose stamp equals stamp_id.
-// lists: 2 * nloc int32 (occupied list, then empty list); counters: two device unsigned ints (zeroed by the caller).
-int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint8_t *stamp, uint32_t stamp_id, int32_t *lists,
-                     unsigned int *counters)
+// list: nloc int32; counter: one device unsigned int (zeroed by the caller).
+int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint8_t *stamp, uint32_t stamp_id, int32_t *list,
+                     unsigned int *counter)
 {
     if (p_hi <= p_lo) return 0;
     if (int rc = nst_ensure(c)) return rc;
-    DirtyArgs a;
-    a.g = c->lat();
-    a.P = c->rp;
-    a.site_rate = c->site_rate; a.dep_rate = c->dep_rate; a.nst = c->nst;
-    a.stamp = stamp; a.stamp_id = stamp_id; a.p_lo = p_lo; a.p_hi = p_hi;
-    a.list_occ = lists; a.list_emp = lists + c->nloc;
-    a.n_occ = counters; a.n_emp = counters + 1;
+    if (int rc = rate_tables_ensure(c)) return rc;
+    DirtyArgs d;
+    d.stamp = stamp; d.stamp_id = stamp_id; d.L = (int)c->n1; d.p_lo = p_lo; d.p_hi = p_hi;
+    d.list = list; d.n_list = counter;
     const int nrows = (p_hi - p_lo) * (int)c->n1;
-    dirty_scan_kernel<<<(nrows + RB_WARPS - 1) / RB_WARPS, RB_WARPS * 32, 0, c->stream>>>(a);
+    dirty_scan_kernel<<<(nrows + RB_WARPS - 1) / RB_WARPS, RB_WARPS * 32, 0, c->stream>>>(d);
     CET_CUDA(cudaGetLastError());
-    dirty_eval_kernel<<<148 * 40, RB_WARPS * 32, 0, c->stream>>>(a);
+    const int64_t nsite = (int64_t)(p_hi - p_lo) * c->plane;
+    const int grid = (int)std::min<int64_t>((nsite + RT_CHUNK * RT_WARPS - 1) / (RT_CHUNK * RT_WARPS), 148 * 5);
+    unsigned int *queue = (unsigned int *)(c->rate_tab + RT_TABLE_DOUBLES) + 1;
+    CET_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned int), c->stream));
+    dirty_eval_kernel<<<grid, RT_THREADS, sizeof(RateSmem), c->stream>>>(tile_args(c), list, counter, queue);
     CET_CUDA(cudaGetLastError());
     return 0;
 }
@@ -288,13 +291,20 @@ int rates_build(cet_ctx *c)
 {
     const int p_lo = c->halo, p_hi = (int)(c->np - c->halo);
     if (int rc = rates_rows(c, p_lo, p_hi)) return rc;
-    RatesArgs a;
-    a.g = c->lat(); a.p_lo = p_lo; a.p_hi = p_hi;
-    const int npl = a.p_hi - a.p_lo;
-    seg_kernel<<<(npl + 3) / 4, 128, 0, c->stream>>>(c->row_occ, c->row_emp, c->row_dep, c->seg, (int)c->n1,
-                                                     a.p_lo, a.p_hi, a.g.i_off, a.g.n0);
+    const int i_off = (int)(c->i_begin - c->halo);
+    RowSumArgs r;
+    r.vox = c->vox; r.site_rate = c->site_rate; r.dep_rate = c->dep_rate;
+    r.row_occ = c->row_occ; r.row_emp = c->row_emp; r.row_dep = c->row_dep; r.row_depcnt = c->row_depcnt;
+    r.L = (int)c->n1; r.p_lo = p_lo; r.p_hi = p_hi;
+    r.top_plane = (c->n0 - 1 - i_off >= p_lo && c->n0 - 1 - i_off < p_hi) ? (int)(c->n0 - 1 - i_off) : -1;
+    const int nrows = (p_hi - p_lo) * (int)c->n1;
+    row_sums_kernel<<<(nrows + RB_WARPS - 1) / RB_WARPS, RB_WARPS * 32, 0, c->stream>>>(r);
     CET_CUDA(cudaGetLastError());
-    total_kernel<<<1, 256, 0, c->stream>>>(c->seg, c->row_depcnt, c->total, a.p_lo, a.p_hi, (int)c->n1,
+    const int npl = p_hi - p_lo;
+    seg_kernel<<<(npl + 3) / 4, 128, 0, c->stream>>>(c->row_occ, c->row_emp, c->row_dep, c->seg, (int)c->n1,
+                                                     p_lo, p_hi, i_off, (int)c->n0);
+    CET_CUDA(cudaGetLastError());
+    total_kernel<<<1, 256, 0, c->stream>>>(c->seg, c->row_depcnt, c->total, p_lo, p_hi, (int)c->n1,
                                            c->i_end == c->n0 ? 1 : 0);
     CET_CUDA(cudaGetLastError());
     c->rates_valid = true;

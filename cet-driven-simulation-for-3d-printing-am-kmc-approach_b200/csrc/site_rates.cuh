@@ -12,19 +12,25 @@
 //   * orientations enter through resident unit vectors v = (sin t cos p, sin t sin p, cos t)
 //     kept in HBM beside theta/phi (kmc_event_rates.py:11-20 recomputes them per pair: 8
 //     trigonometric calls per attachment event); cos(arccos(dot)) (:23,:155) is taken as dot;
-//   * x / y inside a rate is x * rcp(y) with a Newton-refined reciprocal (<= 1 ulp).
+//   * x / y inside a rate is x * rcp(y) with a Newton-refined reciprocal (<= 1 ulp);
+//   * the Arrhenius factors use fast_exp (table of 2^(j/32) + degree-6 polynomial, <= 1 ulp; 11
+//     fp64 instructions instead of libdevice's ~30), and the per-site constant factors are
+//     multiplied first: rate = grad * (nu * boltz), rate = exp(..) * (nu * gfac).
 //
 // The file also compiles for the host (g++, tests/hostsim only — a checker for this arithmetic
 // that needs no GPU; not a product code path).
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 #include "../../include/cetkmc.h"
 
 #if defined(__CUDACC__)
 #define CET_HD __host__ __device__ __forceinline__
+#define CET_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define CET_HD inline
+#define CET_HD_NOINLINE inline
 #endif
 
 namespace cet {
@@ -44,6 +50,89 @@ CET_HD double rcp(double x)
     r = __fma_rn(r, __fma_rn(-x, r, 1.0), r);
     r = __fma_rn(r, __fma_rn(-x, r, 1.0), r);
     return r;
+#else
+    return 1.0 / x;
+#endif
+}
+
+// exp(x): x = (32 m + j) ln2/32 + r, |r| <= ln2/64;  exp(x) = 2^m * 2^(j/32) * (1 + p(r)).
+// Outside |x| < 700 (overflow, gradual underflow, NaN) the library exp is used.
+#define CET_EXP2_TAB_INIT {0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0, \
+    0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0, 0x1.306fe0a31b715p+0, \
+    0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0, 0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, \
+    0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0, 0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0, 0x1.7a11473eb0187p+0, \
+    0x1.82589994cce13p+0, 0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0, \
+    0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0, 0x1.d5818dcfba487p+0, \
+    0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0}
+static const double h_exp2_tab[32] = CET_EXP2_TAB_INIT;
+#if defined(__CUDACC__)
+static __device__ const double d_exp2_tab[32] = CET_EXP2_TAB_INIT;
+#endif
+static CET_HD_NOINLINE double slow_exp(double x) { return exp(x); }   // rare path, kept out of line
+#if defined(__CUDACC__)
+// fast_exp constants in the constant bank: fp64 instructions take them as operands directly (an
+// immediate costs two extra move instructions per constant)
+static __constant__ double c_exp_k[9] = {0x1.71547652b82fep+5, 6755399441055744.0, -0x1.62e42fefa39efp-6, -0x1.abc9e3b39803fp-61,
+                                         0x1.6c16c16c16c17p-10, 0x1.1111111111111p-7, 0x1.5555555555555p-5,
+                                         0x1.5555555555555p-3, 0.5};
+#endif
+CET_HD double fast_exp_t(double x, const double *tab)      // tab: 2^(j/32), j = 0..31 (any address space)
+{
+    if (!(fabs(x) < 700.0)) return slow_exp(x);
+    const double big = 6755399441055744.0;                                  // 1.5 * 2^52: rint by magic add
+    (void)big;
+#if defined(__CUDA_ARCH__)
+    const double tt = __fma_rn(x, c_exp_k[0], c_exp_k[1]);                 // x * 32/ln2
+    const int n = __double2loint(tt);
+    const double nf = tt - c_exp_k[1];
+    double r = __fma_rn(nf, c_exp_k[2], x);                                 // ln2/32 in two parts
+    r = __fma_rn(nf, c_exp_k[3], r);
+    double q = __fma_rn(c_exp_k[4], r, c_exp_k[5]);                         // 1/720, 1/120
+    q = __fma_rn(q, r, c_exp_k[6]);                                         // 1/24
+    q = __fma_rn(q, r, c_exp_k[7]);                                         // 1/6
+    q = __fma_rn(q, r, c_exp_k[8]);
+    const double p = __fma_rn(q, r * r, r);                                 // exp(r) - 1
+    const double t = tab[n & 31];
+    const double y = __fma_rn(t, p, t);
+    return __hiloint2double(__double2hiint(y) + ((n >> 5) << 20), __double2loint(y));
+#else
+    const double tt = fma(x, 0x1.71547652b82fep+5, big);
+    int64_t bits;
+    memcpy(&bits, &tt, 8);
+    const int n = (int)(uint32_t)bits;
+    const double nf = tt - big;
+    double r = fma(nf, -0x1.62e42fefa39efp-6, x);
+    r = fma(nf, -0x1.abc9e3b39803fp-61, r);
+    double q = fma(0x1.6c16c16c16c17p-10, r, 0x1.1111111111111p-7);
+    q = fma(q, r, 0x1.5555555555555p-5);
+    q = fma(q, r, 0x1.5555555555555p-3);
+    q = fma(q, r, 0.5);
+    const double p = fma(q, r * r, r);
+    const double t = tab[n & 31];
+    const double y = fma(t, p, t);
+    int64_t yb;
+    memcpy(&yb, &y, 8);
+    yb += (int64_t)(n >> 5) << 52;
+    double out;
+    memcpy(&out, &yb, 8);
+    return out;
+#endif
+}
+
+#if defined(__CUDA_ARCH__)
+#define CET_EXP2_TAB d_exp2_tab
+#else
+#define CET_EXP2_TAB h_exp2_tab
+#endif
+CET_HD double fast_exp(double x) { return fast_exp_t(x, CET_EXP2_TAB); }
+
+// 1/x with one Newton step (relative error < 2^-45): for quotients that enter a rate as 1 + small * q
+CET_HD double rcp1(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return __fma_rn(r, __fma_rn(-x, r, 1.0), r);
 #else
     return 1.0 / x;
 #endif
@@ -157,72 +246,97 @@ CET_HD int dep_species(const cet_rate_params &P, double r)
     return P.states_w;
 }
 
+// `rate > RATE_THRESHOLD and isfinite(rate)` (kmc_event_rates.py:108,131,157): the rate, or 0 when filtered
+CET_HD double keep_rate(const cet_rate_params &P, double rate)
+{
+    return (rate > P.rate_threshold && rate < INFINITY) ? rate : 0.0;
+}
+
 // ---- occupied site: diffusion (kmc_event_rates.py:79-109) ------------------------------------
-struct OccPrep { double local_T, boltz; };
+// Split into the pieces the dense kernel evaluates separately (per-site exponent argument, one
+// exp shared by both site classes, per-pair rates); occ_prep / emp_prep compose the same pieces,
+// so every consumer produces the same bits.
+struct OccPrep { double local_T, nb; };            // nb = nu * exp(-defect_factor * E_tot / (kT * local_T))
+
+CET_HD int species3(const cet_rate_params &P, int st) { return st == P.states_w ? 0 : st == P.states_re ? 1 : 2; }   // :83-91
+CET_HD double occ_E_tot(const cet_rate_params &P, int sp, int n_bonds)                                              // :105
+{
+    return pymax(P.E_diff[sp] + 0.1 * (double)n_bonds * P.E_b[sp], 0.0);
+}
+CET_HD double occ_exp_arg(int defects, double E_tot, double inv_kTT) { return -(1.0 + (double)defects) * E_tot * inv_kTT; }
 
 CET_HD OccPrep occ_prep(const cet_rate_params &P, int self_state, int defects, double T_self, int n_bonds)
 {
-    double E_b_atom, E_diff_atom;
-    if (self_state == P.states_w) { E_b_atom = P.E_b[0]; E_diff_atom = P.E_diff[0]; }
-    else if (self_state == P.states_re) { E_b_atom = P.E_b[1]; E_diff_atom = P.E_diff[1]; }
-    else { E_b_atom = P.E_b[2]; E_diff_atom = P.E_diff[2]; }
     OccPrep q;
     q.local_T = pymax(T_self, 1.0);
-    const double defect_factor = 1.0 + (double)defects;
-    const double E_tot = pymax(E_diff_atom + 0.1 * (double)n_bonds * E_b_atom, 0.0);
-    q.boltz = exp(-defect_factor * E_tot * rcp(P.kT * q.local_T));
+    const double inv_kTT = rcp(P.kT * q.local_T);
+    q.nb = P.nu * fast_exp(occ_exp_arg(defects, occ_E_tot(P, species3(P, self_state), n_bonds), inv_kTT));
     return q;
 }
 
 // rate of the diffusion event into an empty neighbour whose raw temperature is Tn_raw;
 // returns 0 when the event is filtered (:108)
-CET_HD double diff_pair_rate(const cet_rate_params &P, const OccPrep &q, double Tn_raw)
+CET_HD double diff_pair_rate(const cet_rate_params &P, double local_T, double nb, double Tn_raw)
 {
     const double neighbor_T = pymax(Tn_raw, 1.0);
-    const double dT = fabs(q.local_T - neighbor_T);
+    const double dT = fabs(local_T - neighbor_T);
     const double denom = pymax(P.T_melt - neighbor_T, 1.0);
-    const double grad_factor = 1.0 + 0.1 * dT * rcp(denom);
-    const double rate = P.nu * grad_factor * q.boltz;
-    return (rate > P.rate_threshold && finite_f64(rate)) ? rate : 0.0;
+    const double grad_factor = fma(0.1 * dT, rcp1(denom), 1.0);
+    return keep_rate(P, grad_factor * nb);
 }
 
 // ---- empty site: nucleation + attachment (kmc_event_rates.py:116-158) --------------------------
 struct EmpPrep {
     double nuc_rate;     // 0 when there is no nucleation event
     double inv_kTT;      // 1 / (kT * local_T)
-    double gfac;         // 1 + ANISOTROPY * max(0, grad_z) / max(T_melt - local_T, 1)
+    double ng;           // nu * (1 + ANISOTROPY * max(0, grad_z) / max(T_melt - local_T, 1))
 };
+
+CET_HD double nuc_K_eff(const cet_rate_params &P, int n_imp, int n_in)                      // :126-128
+{
+    const double f_imp = pymin(P.max_imp_fraction, (double)n_imp / (double)(n_in > 1 ? n_in : 1));
+    const double K_eff = P.k_nuc * (1.0 - P.beta_imp_nuc * f_imp);
+    return pymax(0.1 * P.k_nuc, pymin(P.k_nuc, K_eff));
+}
+CET_HD bool nuc_exists(const cet_rate_params &P, double local_T) { return (P.T_melt - local_T) > P.delta_T_c; }   // :120
+CET_HD double nuc_exp_arg(const cet_rate_params &P, double local_T, double K_eff, double inv_kTT)                  // :129-130
+{
+    const double d = (P.T_melt - local_T) + 1e-6;
+    const double barrier = K_eff * rcp(pymax(d * d, 1e-6));
+    return -barrier * inv_kTT;
+}
+CET_HD double nuc_from_exp(const cet_rate_params &P, double e)                                                     // :130-131
+{
+    return keep_rate(P, P.i0 * e);
+}
+CET_HD double emp_ng(const cet_rate_params &P, double local_T, double T_km, double T_kp)                           // :151-154
+{
+    const double grad_z = (T_kp - T_km) * 0.5;
+    const double gfac = 1.0 + P.anisotropy * (pymax(0.0, grad_z) * rcp1(pymax(P.T_melt - local_T, 1.0)));
+    return P.nu * gfac;
+}
 
 CET_HD EmpPrep emp_prep(const cet_rate_params &P, double T_self, double T_km, double T_kp, int n_imp, int n_in)
 {
     EmpPrep q;
     const double local_T = pymax(T_self, 1.0);
-    const double dT = P.T_melt - local_T;
     q.inv_kTT = rcp(P.kT * local_T);
     q.nuc_rate = 0.0;
-    if (dT > P.delta_T_c) {                                      // :120-132
-        const double f_imp = pymin(P.max_imp_fraction, (double)n_imp / (double)(n_in > 1 ? n_in : 1));
-        double K_eff = P.k_nuc * (1.0 - P.beta_imp_nuc * f_imp);
-        K_eff = pymax(0.1 * P.k_nuc, pymin(P.k_nuc, K_eff));
-        const double barrier = K_eff * rcp(pymax((dT + 1e-6) * (dT + 1e-6), 1e-6));
-        const double rate = P.i0 * exp(-barrier * q.inv_kTT);
-        if (rate > P.rate_threshold && finite_f64(rate)) q.nuc_rate = rate;
-    }
-    const double grad_z = (T_kp - T_km) * 0.5;                   // :151-154
-    q.gfac = 1.0 + P.anisotropy * (pymax(0.0, grad_z) * rcp(pymax(P.T_melt - local_T, 1.0)));
+    if (nuc_exists(P, local_T))
+        q.nuc_rate = nuc_from_exp(P, fast_exp(nuc_exp_arg(P, local_T, nuc_K_eff(P, n_imp, n_in), q.inv_kTT)));
+    q.ng = emp_ng(P, local_T, T_km, T_kp);
     return q;
 }
 
-// rate of the attachment event copying occupied neighbour n (species index ia = 0 W, 1 Re, 2 C);
-// returns 0 when filtered (:157)
-CET_HD double att_pair_rate(const cet_rate_params &P, const EmpPrep &q, int ia, double sx, double sy, double sz,
-                            double nx, double ny, double nz)
+// rate of the attachment event copying an occupied neighbour of species energy hE = 0.5 * E_b[ia]
+// (ia = 0 W, 1 Re, 2 C); returns 0 when filtered (:157)
+CET_HD double att_pair_rate(const cet_rate_params &P, double hE, double inv_kTT, double ng, double sx, double sy,
+                            double sz, double nx, double ny, double nz, const double *exp_tab = CET_EXP2_TAB)
 {
-    double dot = sx * nx + sy * ny + sz * nz;
+    double dot = fma(sz, nz, fma(sy, ny, sx * nx));
     dot = pymax(pymin(dot, 1.0), -1.0);
-    const double E_att = 0.5 * P.E_b[ia] * (1.0 - dot);
-    const double rate = P.nu * exp(-E_att * q.inv_kTT) * q.gfac;
-    return (rate > P.rate_threshold && finite_f64(rate)) ? rate : 0.0;
+    const double E_att = hE * (1.0 - dot);
+    return keep_rate(P, fast_exp_t(-E_att * inv_kTT, exp_tab) * ng);
 }
 
 CET_HD int species_index(const cet_rate_params &P, int st)
@@ -283,7 +397,7 @@ CET_HD void site_events(const Lat &g, const cet_rate_params &P, int i, int j, in
 #pragma unroll 1
         for (int o = 0; o < 14; ++o) {
             if (!(inb >> o & 1u) || ((nst >> (4 * o)) & 15) != 0) continue;
-            const double rate = diff_pair_rate(P, q, g.T[g.nb(s, o)]);
+            const double rate = diff_pair_rate(P, q.local_T, q.nb, g.T[g.nb(s, o)]);
             if (rate != 0.0) emit((int)CET_EV_DIFF, o, rate, self);
         }
         return;
@@ -303,7 +417,7 @@ CET_HD void site_events(const Lat &g, const cet_rate_params &P, int i, int j, in
         if (na == 0 || ia < 0) continue;
         const int64_t t = g.nb(s, o);
         const Vec4 nv = g.v[t];
-        const double rate = att_pair_rate(P, q, ia, sx, sy, sz, nv.x, nv.y, nv.z);
+        const double rate = att_pair_rate(P, 0.5 * P.E_b[ia], q.inv_kTT, q.ng, sx, sy, sz, nv.x, nv.y, nv.z);
         if (rate != 0.0) emit((int)CET_EV_ATT, o, rate, na);
     }
 }

@@ -18,13 +18,16 @@ def main():
         N = L ** 3
         tp = thermal_params(1e-6, nan_to_num=True)
         for name, fn, bytes_per_site in (("thermal_cet", lambda: ctx.thermal_cet(tp), 16),
-                                         ("rates_build", lambda: ctx.rates_build(), 33)):
+                                         ("rates_build", lambda: ctx.rates_build(), 41)):
             for _ in range(3): fn()
+            ctx.profile_enable(True)
             ctx.timer_begin()
             n = 10
             for _ in range(n): fn()
             ms = ctx.timer_end_ms() / n
-            print(f"  {name}: {ms:.3f} ms  {N/ms*1e3:.3e} sites/s  {N*bytes_per_site/ms/1e6:.0f} GB/s algorithmic", flush=True)
+            ctx.profile_enable(False)
+            kms = ctx.profile_read("rates" if name == "rates_build" else "thermal")[0] / n
+            print(f"  {name}: {ms:.3f} ms (kernel {kms:.3f} ms)  {N/ms*1e3:.3e} sites/s  {N*bytes_per_site/kms/1e6:.0f} GB/s algorithmic", flush=True)
         ctx.upload(T=T)
         sp = cetkmc._lib.SweepParams()
         for eps, pmax in ((0.02, 0.25), (0.005, 0.1), (0.001, 0.05)):
@@ -42,10 +45,13 @@ def main():
         st = np.zeros((L, L, L), np.uint8); st[:, :, 0] = (np.random.default_rng(0).random((L, L)) < 0.02)
         ctx.upload_packed(st); ctx.upload(theta=np.zeros((L, L, L)), phi=np.zeros((L, L, L)))
         for _ in range(3): ctx.rates_build()
+        ctx.profile_enable(True)
         ctx.timer_begin()
         for _ in range(10): ctx.rates_build()
         ms = ctx.timer_end_ms() / 10
-        print(f"  rates_build(fresh): {ms:.3f} ms  {N/ms*1e3:.3e} sites/s  {N*33/ms/1e6:.0f} GB/s algorithmic", flush=True)
+        ctx.profile_enable(False)
+        kms = ctx.profile_read("rates")[0] / 10
+        print(f"  rates_build(fresh): {ms:.3f} ms (kernel {kms:.3f} ms)  {N/ms*1e3:.3e} sites/s  {N*41/kms/1e6:.0f} GB/s algorithmic (41 B/site)", flush=True)
         ctx.close()
 
 main()

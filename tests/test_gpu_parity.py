@@ -144,6 +144,34 @@ def test_site_rates_and_total_vs_oracle(cet, oracle, L, ups):
 
 
 # ---------------------------------------------------------------- level 2: exact BKL, injected draws
+@pytest.mark.parametrize("L", [36, 66])
+def test_site_rates_dense_interfaces(cet, oracle, L):
+    """Rows of solid separated by empty rows: every occupied site owns 12 diffusion events and
+    every empty one up to 8 attachment events, more pairs per 32 sites than the warp's pair slots
+    hold (the two-half-tile path of rate_tile.cuh); general orientations on the empty sites too."""
+    from cetkmc._config import rate_params
+    rng = np.random.default_rng(L)
+    i, j = np.arange(L)[:, None, None], np.arange(L)[None, :, None]
+    st = np.where((i % 3 == 0) & (j % 3 == 0), rng.choice(np.array([1, 2, 3, 4]), size=(L, L, L), p=[.7, .15, .1, .05]), 0)
+    st = np.ascontiguousarray(np.broadcast_to(st, (L, L, L))).astype(np.int64)
+    th = rng.uniform(0, np.pi, (L, L, L)); ph = rng.uniform(0, 2 * np.pi, (L, L, L))
+    T = 2800 + 895.0 * rng.random((L, L, L))
+    df = ((st == 3) & (rng.random((L, L, L)) < 0.3)).astype(np.int64)
+    ctx = cet.Context(L=L)
+    ctx.set_rate_params(rate_params(0.1))
+    ctx.upload(state=st, theta=th, phi=ph, T=T, defects=df)
+    ctx.rates_build()
+    sr, dr = ctx.rates_download()
+    o_sr, o_dep, n_ev, _ = oracle.site_rates(st, th, ph, T, df, L, oracle.make_params(0.1))
+    np.testing.assert_allclose(sr, o_sr, rtol=RTOL, atol=0.0)
+    assert np.array_equal(np.isnan(dr), np.isnan(o_dep))
+    # atol: libdevice's exp flushes results in the last subnormal binades (~1e-323) to zero, libm does not
+    np.testing.assert_allclose(np.nan_to_num(dr), np.nan_to_num(o_dep), rtol=RTOL, atol=1e-300)
+    # the per-event list (site_events code path) agrees with the dense sums
+    ev = oracle.event_rates(st, th, ph, T, df, L, oracle.make_params(0.1))
+    assert ctx.events_count()[0] == ev["rate"].size
+
+
 @pytest.mark.parametrize("L,steps,defect_fraction,c,ups", [(12, 400, 0.02, 0.1, 0), (16, 300, 0.0, 0.0, 2),
                                                               (20, 250, 3e-3, 0.2, 30)])
 def test_kmc_run_bit_exact_vs_oracle(cet, oracle, L, steps, defect_fraction, c, ups):
