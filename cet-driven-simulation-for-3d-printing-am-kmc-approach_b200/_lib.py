@@ -270,8 +270,15 @@ class Context:
         self._chk(p, "packed")
         check(lib().cet_upload_packed(self._h, _ptr(p)), "cet_upload_packed")
 
-    def download_packed(self):
-        p = np.empty(self.owned_shape, np.uint8)
+    def download_packed(self, out=None):
+        """Packed state (state | defects << 4); `out`: a C-contiguous uint8 array of the owned shape
+        to fill (e.g. page-locked memory) instead of a fresh pageable one."""
+        if out is None:
+            p = np.empty(self.owned_shape, np.uint8)
+        else:
+            p = out
+            if p.dtype != np.uint8 or not p.flags.c_contiguous or tuple(p.shape) != self.owned_shape:
+                raise ValueError(f"packed: need C-contiguous uint8 array of shape {self.owned_shape}")
         check(lib().cet_download_packed(self._h, _ptr(p)), "cet_download_packed")
         return p
 

@@ -214,18 +214,24 @@ def slab_bounds(L: int, world: int, rank: int):
 SWEEP_HALO = 6       # ghost planes per side a slab needs for one communication per sweep
 
 
-def run_kmc_sublattice_slab(ctx, packed, theta, phi, T, n_sweeps, sweep_params, thermal=None):
+def run_kmc_sublattice_slab(ctx, packed, theta, phi, T, n_sweeps, sweep_params, thermal=None, out=None):
     """One call = upload this rank's planes from host memory (packed uint8 state | defects << 4,
     float64 theta / phi / T), refresh the ghost planes, run n_sweeps synchronous-sublattice
     sweeps, and read the lattice back.  `ctx` is an existing cetkmc.Context (already bound to its
-    communicator when the lattice spans several GPUs)."""
+    communicator when the lattice spans several GPUs).  `out` (optional): dict with preallocated
+    `packed` / `theta` / `phi` arrays of the owned shape that receive the result — with page-locked
+    buffers on both sides the copies run at PCIe speed instead of the pageable-memory rate."""
     ctx.upload_packed(packed)
     ctx.upload(theta=theta, phi=phi, T=T)
     ctx.halo_exchange(7)
-    out = ctx.sweep_run(n_sweeps, sweep_params, thermal)
-    out["packed"] = ctx.download_packed()
-    out.update(ctx.download(theta=True, phi=True))
-    return out
+    res = ctx.sweep_run(n_sweeps, sweep_params, thermal)
+    if out is None:
+        res["packed"] = ctx.download_packed()
+        res.update(ctx.download(theta=True, phi=True))
+    else:
+        res["packed"] = ctx.download_packed(out=out["packed"])
+        res.update(ctx.download(out=dict(theta=out["theta"], phi=out["phi"])))
+    return res
 
 
 def run_kmc_sublattice(state, theta, phi, T, defects_mask=None, n_sweeps=100, impurity_c=0.0,
