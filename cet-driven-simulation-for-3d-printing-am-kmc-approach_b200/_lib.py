@@ -97,6 +97,8 @@ SIGNATURES = {
     "cet_kmc_run": [_VP, _I64, _I64, _F64, C.POINTER(ThermalParams), _I32, _VP, _I64, _VP, _I64,
                     _VP, _I64, _F64, C.POINTER(KmcResult), _VP, _VP, _VP, _VP, _VP, _VP],
     "cet_sweep_reset": [_VP],
+    "cet_sweep_get_state": [_VP, C.POINTER(_I64), C.POINTER(_F64), C.POINTER(_F64)],
+    "cet_sweep_set_state": [_VP, _I64, _F64, _F64],
     "cet_sweep_run": [_VP, _I64, C.POINTER(SweepParams), C.POINTER(ThermalParams),
                       C.POINTER(SweepResult)],
     "cet_comm_unique_id": [_VP],
@@ -104,6 +106,8 @@ SIGNATURES = {
     "cet_comm_destroy": [_VP],
     "cet_halo_exchange": [_VP, C.c_int],
     "cet_allreduce_f64": [_VP, _VP, C.c_int, C.c_int],
+    "cet_defects_refresh": [_VP, _VP, _I64, C.c_uint64, C.c_uint32, _F64, _F64, _F64, _F64, _I32, _I32, _I32,
+                            C.POINTER(_I64), C.POINTER(_I64)],
     "cet_grains_label": [_VP, _F64, C.POINTER(_I64)],
     "cet_grains_stats": [_VP, _I64, _VP, _VP, _VP, _VP],
     "cet_grains_download_labels": [_VP, _VP],
@@ -382,6 +386,21 @@ class Context:
         check(lib().cet_allreduce_f64(self._h, _ptr(v), v.size, op), "cet_allreduce_f64")
         return v
 
+    # -- defects (defects.py on the resident lattice) ------------------------------------------------
+    def defects_refresh(self, draws=None, seed=0, epoch=0, prob_base=0.12, e_mig=0.3, kT=8.617333262e-5,
+                        T_default=2800.0, carbon_id=3, defect_id=4, apply_to_state=False):
+        """defects.track_defects / introduce_defects (defects.py:4-31) in place: the defect mask of
+        the resident lattice is redrawn.  draws: the reference's draw stream (one per carbon site, C
+        order), or None for the device's Philox stream keyed by (seed, epoch, site).
+        Returns (n_carbon, n_defects)."""
+        d = None if draws is None else np.ascontiguousarray(draws, dtype=np.float64)
+        nc, nd = C.c_int64(0), C.c_int64(0)
+        check(lib().cet_defects_refresh(self._h, _ptr(d), 0 if d is None else d.size, int(seed), int(epoch),
+                                        float(prob_base), float(e_mig), float(kT), float(T_default), int(carbon_id),
+                                        int(defect_id), 1 if apply_to_state else 0, C.byref(nc), C.byref(nd)),
+              "cet_defects_refresh")
+        return nc.value, nd.value
+
     # -- grains (utils.get_clusters on the resident lattice) ------------------------------------
     def grains(self, theta_threshold=0.5, labels=False):
         """Grains of the resident lattice in the reference's cluster order (raster order of each
@@ -410,6 +429,16 @@ class Context:
         n = C.c_int64(0)
         check(lib().cet_debug_nst_mismatches(self._h, C.byref(n)), "cet_debug_nst_mismatches")
         return n.value
+
+    def sweep_state(self):
+        """(sweep_index, tau, time) of the sweep clock — see sweep_set_state."""
+        i, tau, t = C.c_int64(0), C.c_double(0.0), C.c_double(0.0)
+        check(lib().cet_sweep_get_state(self._h, C.byref(i), C.byref(tau), C.byref(t)), "cet_sweep_get_state")
+        return i.value, tau.value, t.value
+
+    def sweep_set_state(self, sweep_index, tau, time):
+        """Restore the sweep clock of a checkpoint: the resumed run continues bit for bit."""
+        check(lib().cet_sweep_set_state(self._h, int(sweep_index), float(tau), float(time)), "cet_sweep_set_state")
 
     def sweep_reset(self):
         check(lib().cet_sweep_reset(self._h), "cet_sweep_reset")

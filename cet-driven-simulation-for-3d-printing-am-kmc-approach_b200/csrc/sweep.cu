@@ -522,6 +522,42 @@ extern "C" int cet_sweep_reset(cet_ctx *c)
     return 0;
 }
 
+// Checkpoint / resume of the sweep clock: the running sweep counter (the Philox key of the next
+// sweep), the interval tau the next sweep will use and the accumulated time.  With the lattice
+// restored and these three values set, a resumed run continues bit for bit (the resident rates are
+// rebuilt densely, which equals the refreshed rates bit for bit).
+extern "C" int cet_sweep_get_state(cet_ctx *c, int64_t *sweep_index, double *tau, double *time)
+{
+    CET_REQUIRE(c, "cet_sweep_get_state: NULL ctx");
+    cet::DeviceGuard dg(c->device);
+    SweepState h;
+    memset(&h, 0, sizeof(h));
+    if (c->sweep) {
+        CET_CUDA(cudaMemcpyAsync(&h, c->sweep, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CET_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if (sweep_index) *sweep_index = c->sweep_index;
+    if (tau) *tau = h.tau;
+    if (time) *time = h.time;
+    return 0;
+}
+
+extern "C" int cet_sweep_set_state(cet_ctx *c, int64_t sweep_index, double tau, double time)
+{
+    CET_REQUIRE(c && sweep_index >= 0, "cet_sweep_set_state: bad argument");
+    cet::DeviceGuard dg(c->device);
+    if (int rc = sweep_alloc(c)) return rc;
+    SweepState h;
+    CET_CUDA(cudaMemcpyAsync(&h, c->sweep, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CET_CUDA(cudaStreamSynchronize(c->stream));
+    h.tau = tau; h.time = time; h.terminated = 0;
+    CET_CUDA(cudaMemcpyAsync(c->sweep, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+    CET_CUDA(cudaStreamSynchronize(c->stream));
+    c->sweep_index = sweep_index;
+    c->sweep_rates_valid = false;
+    return 0;
+}
+
 extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_params *sp,
                              const cet_thermal_params *tp, cet_sweep_result *res)
 {

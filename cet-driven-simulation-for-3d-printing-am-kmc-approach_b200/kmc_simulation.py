@@ -37,6 +37,7 @@ try:
     from defects import introduce_defects                 # type: ignore
 except Exception:                                         # noqa: BLE001
     introduce_defects = _host.introduce_defects
+from . import defects as _gpu_defects                     # the 200-step mask refresh runs on the resident lattice
 # Observables: grains are clustered on the GPU from the resident lattice (csrc/grains.cu).
 # CETKMC_METRICS=host selects the NumPy/SciPy restatement in _host.py, CETKMC_METRICS=reference
 # the caller's own metrics.py (pure-Python DFS, utils.py:28-84).
@@ -64,20 +65,27 @@ def _replay(stream_state_setter, state, draw, n):
 
 
 def _metrics_row(step, total_time, state, atom_type, theta, phi, defects_mask, nucleation_count,
-                 cet_detected, consts, ctx=None):
+                 cet_detected, consts, ctx=None, verbose=True):
     """kmc_simulation.py:341-378 — one metrics.csv row."""
     G, R, R_phys, G_over_R_phys = consts
     if ctx is not None and _METRICS_MODE == "gpu":
-        m = compute_metrics(state, theta, phi, defects=defects_mask, voxel_size=constants.VOXEL_SIZE, ctx=ctx)
+        counts = ctx.counts()
+        n_sites = int(np.prod(ctx.owned_shape))
+        m = _gpu_metrics.metrics_from_grains(ctx.grains(0.5), n_sites, voxel_size=constants.VOXEL_SIZE)
+        n_w, n_re, n_c = int(counts[1]), int(counts[2]), int(counts[3])
+        defect_voxels = int(counts[constants.DEFECT_ID])
     else:
         m = compute_metrics(state, theta, phi, defects=defects_mask, voxel_size=constants.VOXEL_SIZE)
-    defect_voxels = int(np.sum(atom_type == constants.DEFECT_ID))
+        n_w, n_re, n_c = int((state == 1).sum()), int((state == 2).sum()), int((state == 3).sum())
+        defect_voxels = int(np.sum(atom_type == constants.DEFECT_ID))
+        n_sites = atom_type.size
     m["Defect_voxel_count"] = defect_voxels
-    m["DefectDensity"] = float(defect_voxels / atom_type.size)
+    m["DefectDensity"] = float(defect_voxels / n_sites)
     newly = (not cet_detected) and detect_CET_transition(m)
     if newly:
         cet_detected = True
-        print(f"CET detected at step {step} (G/R={G / R:.2e})")
+        if verbose:
+            print(f"CET detected at step {step} (G/R={G / R:.2e})")
     # compute_CET(state, theta, phi) re-clusters the same lattice and applies the same two
     # thresholds to AspectRatio / EquiaxedFraction (metrics.py:99-105); reuse m instead.
     cet_cls = "Equiaxed" if detect_CET_transition(m) else "Columnar"
@@ -86,14 +94,14 @@ def _metrics_row(step, total_time, state, atom_type, theta, phi, defects_mask, n
         "AspectRatio": m["AspectRatio"], "EquiaxedFraction": m["EquiaxedFraction"],
         "NucleationDensity": m["NucleationDensity"], "DefectDensity": m["DefectDensity"],
         "AvgGrainSize": m["AvgGrainSize"], "GrainCount": m["GrainCount"],
-        "W_Count": int((state == 1).sum()), "Re_Count": int((state == 2).sum()),
-        "C_Count": int((state == 3).sum()), "NucleationCount": nucleation_count,
+        "W_Count": n_w, "Re_Count": n_re, "C_Count": n_c, "NucleationCount": nucleation_count,
         "G_over_R": (G / R) if R > 0 else np.inf, "G_phys": G, "R_phys": R_phys,
         "G_over_R_phys": G_over_R_phys, "CET_Class": cet_cls, "CET_Detected": cet_detected,
     }
-    print(f"Step {step}: AR={row['AspectRatio']:.2f}, EqFrac={row['EquiaxedFraction']:.2f}, "
-          f"NucDens={row['NucleationDensity']:.3e}, DefectDens={row['DefectDensity']:.3e}, "
-          f"CET={row['CET_Class']}, Detected={row['CET_Detected']}, Time={row['Time']:.2e}s")
+    if verbose:
+        print(f"Step {step}: AR={row['AspectRatio']:.2f}, EqFrac={row['EquiaxedFraction']:.2f}, "
+              f"NucDens={row['NucleationDensity']:.3e}, DefectDens={row['DefectDensity']:.3e}, "
+              f"CET={row['CET_Class']}, Detected={row['CET_Detected']}, Time={row['Time']:.2e}s")
     return row, cet_detected
 
 
@@ -110,6 +118,13 @@ def _write_csv(rows, output_dir):
             w = csv.DictWriter(f, fieldnames=list(rows[0].keys()))
             w.writeheader()
             w.writerows(rows)
+    # plot_cet.py:26 globs outputs/impurity_c_*/metrics_*.csv while the driver writes metrics.csv
+    # (kmc_simulation.py:393): for main.py's `impurity_c_<pct>` prefixes the file is also written
+    # under the name the plotting script looks for
+    base = os.path.basename(os.path.normpath(output_dir))
+    if base.startswith("impurity_c_") and base.rsplit("_", 1)[-1].isdigit():
+        import shutil
+        shutil.copyfile(path, os.path.join(output_dir, f"metrics_{base.rsplit('_', 1)[-1]}.csv"))
     print(f"Metrics saved to {path}")
     return path
 
@@ -187,15 +202,23 @@ def run_kmc(L: int = LATTICE_SIZE, n_steps: int = N_STEPS, temp: float = T_SUB,
                 terminated = True
                 break
             last_step = step - 1
-            ctx.download(out=dict(state=state, atom_type=atom_type, theta=theta, phi=phi, T=T))
-            if last_step % every == 0:                                                # :335-338
-                defects_mask, _ = introduce_defects(state, atom_type, T, apply_to_state=False)
-                ctx.upload(defects=defects_mask)
-            row, cet_detected = _metrics_row(last_step, total_time, state, atom_type, theta, phi,
-                                             defects_mask, nucleation_count, cet_detected, consts, ctx=ctx)
+            if _METRICS_MODE == "gpu":
+                # resident cadence (kmc_simulation.py:335-389): the mask refresh, the clustering and the
+                # species counts all run on the device; nothing but the row's scalars crosses PCIe
+                if last_step % every == 0:                                            # :335-338
+                    _gpu_defects.refresh_resident(ctx)
+                row, cet_detected = _metrics_row(last_step, total_time, None, None, None, None, None,
+                                                 nucleation_count, cet_detected, consts, ctx=ctx)
+            else:
+                ctx.download(out=dict(state=state, atom_type=atom_type, theta=theta, phi=phi, T=T))
+                if last_step % every == 0:                                            # :335-338
+                    defects_mask, _ = introduce_defects(state, atom_type, T, apply_to_state=False)
+                    ctx.upload(defects=defects_mask)
+                row, cet_detected = _metrics_row(last_step, total_time, state, atom_type, theta, phi,
+                                                 defects_mask, nucleation_count, cet_detected, consts, ctx=ctx)
             rows.append(row)
+        ctx.download(out=dict(state=state, atom_type=atom_type, theta=theta, phi=phi, T=T))
         if terminated:
-            ctx.download(out=dict(state=state, atom_type=atom_type, theta=theta, phi=phi, T=T))
             last_step = step
         _write_csv(rows, output_dir)
         print(f"Completed {last_step + 1} steps in {total_time:.2e} s")

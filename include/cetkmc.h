@@ -167,6 +167,10 @@ int cet_kmc_run(cet_ctx *ctx, int64_t step0, int64_t n_steps, double defect_frac
 int cet_sweep_run(cet_ctx *ctx, int64_t n_sweeps, const cet_sweep_params *sp,
                   const cet_thermal_params *tp, cet_sweep_result *res);
 int cet_sweep_reset(cet_ctx *ctx); /* zero the sweep counter, clock, tau and event counters */
+/* Checkpoint / resume of the sweep clock: running sweep counter (the Philox key of the next sweep),
+ * the interval tau the next sweep will use, the accumulated time. */
+int cet_sweep_get_state(cet_ctx *ctx, int64_t *sweep_index, double *tau, double *time);
+int cet_sweep_set_state(cet_ctx *ctx, int64_t sweep_index, double tau, double time);
 
 /* ---- z-slab decomposition over the GPUs of one box (NCCL over NVLink) ---- */
 int cet_comm_unique_id(void *id128);
@@ -175,6 +179,17 @@ int cet_comm_destroy(cet_ctx *ctx);
 /* fields bitmask: 1 state, 2 theta+phi, 4 T */
 int cet_halo_exchange(cet_ctx *ctx, int fields);
 int cet_allreduce_f64(cet_ctx *ctx, double *inout_host, int n, int op /* 0 sum, 1 max */);
+
+/* ---- defects.py:4-31 track_defects / introduce_defects on the resident lattice ----
+ * Rewrites the defect mask (high nibble of the voxel byte): 0 everywhere, and on carbon sites
+ * u < clip(prob_base * exp(-e_mig / (kT * T')), 0, 1) with T' = T if T > 0 else T_default.
+ * draws != NULL: the q-th carbon site in C order takes draws[q] (the reference's NumPy stream,
+ * defects.py:18; n_draws >= number of carbon sites, whole-lattice contexts only); draws == NULL:
+ * Philox keyed by (seed, epoch, global site).  apply_to_state != 0 also turns the masked sites into
+ * defect_id (defects.py:28-29).  n_carbon = draws consumed, n_defects = sites with the mask set. */
+int cet_defects_refresh(cet_ctx *ctx, const double *draws, int64_t n_draws, uint64_t seed, uint32_t epoch,
+                        double prob_base, double e_mig, double kT, double T_default, int32_t carbon_id,
+                        int32_t defect_id, int32_t apply_to_state, int64_t *n_carbon, int64_t *n_defects);
 
 /* ---- utils.get_clusters / metrics.compute_metrics (utils.py:28-84,104-111; metrics.py:41-96) ----
  * Grains = connected components of occupied sites (state != 0) joined by the 14-offset
