@@ -107,8 +107,7 @@ struct cet_ctx {
     size_t cap_log = 0;
 
     // sweep mode
-    uint8_t *stamp = nullptr;         // per site: id (1..255, cycling) of the last sweep that requested a refresh
-    int64_t stamp_cycle = 0;
+    uint32_t *stamp = nullptr;        // refresh requests of the current sweep, one bit per local site
     int32_t *dirty = nullptr, *fired = nullptr;
     size_t cap_dirty = 0, cap_fired = 0;
     cet::SweepState *sweep = nullptr;

@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(RB_WARPS * 32) row_sums_kernel(const RowSumArg
 
 // Neighbour-rate refresh (sweep.cu): the sites stamped in this sweep are re-evaluated with the same
 // tile code as the dense pass.  Two kernels:
-//   scan  streams the stamp array (1 B/site) and compacts the stamped sites into one global list
-//         (one atomic per 8-row CTA, so the list stays roughly in lattice order: a tile of 32
+//   scan  streams the stamp bitmap (1 bit/site) and compacts the stamped sites into one global list
+//         (one atomic per 8192-site CTA, so the list stays roughly in lattice order: a tile of 32
 //         entries comes from one or two adjacent rows and its neighbour gathers coalesce;
 //         emitting the list in 8 x 8 x L blocks instead was measured and is slower, 1.43 vs 1.39 ms
 //         at 0.5 % N events per sweep and 6.2 vs 3.2 ms at 2 % N);
@@ -120,87 +120,57 @@ __global__ void __launch_bounds__(RB_WARPS * 32) row_sums_kernel(const RowSumArg
 //         neighbourhood changed), so the apply kernel needs no atomics to maintain the cache.
 // Results go straight to site_rate / dep_rate; the BKL row sums are not maintained.
 struct DirtyArgs {
-    const uint8_t *stamp;
-    uint32_t stamp_id;
-    int L, p_lo, p_hi;
+    const uint32_t *stamp;            // one bit per local site
+    int s_lo, s_hi;                   // local linear site range to scan
     int32_t *list;                    // capacity: one entry per local site
     unsigned int *n_list;             // list length (device counter)
 };
 
-constexpr int DS_STAGE = 2048;     // staged list entries per CTA (8 rows)
+constexpr int DS_STAGE = 2048;     // staged list entries per CTA (256 words = 8192 sites)
 
 __global__ void __launch_bounds__(RB_WARPS * 32) dirty_scan_kernel(const __grid_constant__ DirtyArgs a)
 {
     __shared__ int s_list[DS_STAGE];                                // staging; spills are appended directly
     __shared__ unsigned int c_list, b_list, s_first_spill;
-    const int L = a.L;
     if (threadIdx.x == 0) { c_list = 0; s_first_spill = 0xffffffffu; }
     __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int row = blockIdx.x * RB_WARPS + wid;             // one row per warp, 8 consecutive rows per CTA
-    const bool vec = (L % 16) == 0;                          // rows are then 16-byte aligned in the stamp array
-    const uint8_t want = (uint8_t)a.stamp_id;
-    if (row < (a.p_hi - a.p_lo) * L) {
-        const int rbase = (a.p_lo * L + row) * L;
-        for (int k0 = 0; k0 < L; k0 += 512) {
-            const int kb = k0 + 16 * lane;                   // this lane's sixteen consecutive sites
-            uint32_t wv[4];
-            if (kb >= L) {
-                wv[0] = wv[1] = wv[2] = wv[3] = 0x01010101u * (uint8_t)~want;
-            } else if (vec) {
-                const uint4 v4 = *reinterpret_cast<const uint4 *>(a.stamp + rbase + kb);
-                wv[0] = v4.x; wv[1] = v4.y; wv[2] = v4.z; wv[3] = v4.w;
-            } else {
+    const int lane = threadIdx.x & 31;
+    const int wi = (a.s_lo >> 5) + blockIdx.x * (RB_WARPS * 32) + threadIdx.x;      // this thread's 32 sites
+    const int b0 = wi << 5;
+    uint32_t match = b0 < a.s_hi ? a.stamp[wi] : 0u;
+    if (b0 < a.s_lo) match &= 0xffffffffu << (a.s_lo - b0);                       // range ends inside a word
+    if (b0 + 32 > a.s_hi && b0 < a.s_hi) match &= 0xffffffffu >> (b0 + 32 - a.s_hi);
+    // ordered compaction of the warp's 1024 sites: warp scan of the match counts, one counter update per warp
+    const int nm = __popc(match);
+    int inc = nm;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    wv[q] = 0;
-                    for (int b = 0; b < 4; ++b)
-                        if (kb + 4 * q + b < L) wv[q] |= (uint32_t)(a.stamp[rbase + kb + 4 * q + b] == want ? want : (uint8_t)~want) << (8 * b);
-                        else wv[q] |= (uint32_t)(uint8_t)~want << (8 * b);
-                }
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    const int tot = __shfl_sync(0xffffffffu, inc, 31);
+    if (tot) {
+        unsigned int q0 = 0;
+        int spill = 0;
+        if (lane == 0) {
+            q0 = atomicAdd(&c_list, (unsigned)tot);
+            if (q0 + tot > DS_STAGE) {                                  // staging full: append directly
+                atomicMin(&s_first_spill, q0);
+                q0 = atomicAdd(a.n_list, (unsigned)tot);
+                spill = 1;
             }
-            // one bit per matching byte (exact zero-byte test on wv ^ rep), then visit the matches only
-            const uint32_t rep = 0x01010101u * want;
-            uint32_t match = 0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t x = wv[q] ^ rep;                                  // zero byte <=> match
-                const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 in every zero byte
-                match |= (((z >> 7) & 1u) | ((z >> 14) & 2u) | ((z >> 21) & 4u) | ((z >> 28) & 8u)) << (4 * q);
-            }
-            // k-ordered compaction of the row: warp scan of the match counts, one counter update per warp
-            const int nm = __popc(match);
-            int inc = nm;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += t;
-            }
-            const int tot = __shfl_sync(0xffffffffu, inc, 31);
-            if (tot == 0) continue;
-            unsigned int q0 = 0;
-            int spill = 0;
-            if (lane == 0) {
-                q0 = atomicAdd(&c_list, (unsigned)tot);
-                if (q0 + tot > DS_STAGE) {                                  // staging full: append directly
-                    atomicMin(&s_first_spill, q0);
-                    q0 = atomicAdd(a.n_list, (unsigned)tot);
-                    spill = 1;
-                }
-            }
-            q0 = __shfl_sync(0xffffffffu, q0, 0);
-            spill = __shfl_sync(0xffffffffu, spill, 0);
-            int *dst = (spill ? a.list : s_list) + q0 + (inc - nm);
-            while (match) {
-                const int e = __ffs(match) - 1;
-                match &= match - 1;
-                *dst++ = rbase + kb + e;
-            }
+        }
+        q0 = __shfl_sync(0xffffffffu, q0, 0);
+        spill = __shfl_sync(0xffffffffu, spill, 0);
+        int *dst = (spill ? a.list : s_list) + q0 + (inc - nm);
+        while (match) {
+            const int e = __ffs(match) - 1;
+            match &= match - 1;
+            *dst++ = b0 + e;
         }
     }
     __syncthreads();
-    // the staged prefix is contiguous up to the first group that did not fit (its counter value q0
-    // satisfies q0 <= DS_STAGE < q0 + nm): entries [0, q0) are staged, q0 = the smallest such start
+    // the staged prefix is contiguous up to the first warp that did not fit
     const unsigned int n = min(c_list, s_first_spill);
     if (threadIdx.x == 0) b_list = n ? atomicAdd(a.n_list, n) : 0u;
     __syncthreads();
@@ -264,19 +234,18 @@ int rates_rows(cet_ctx *c, int p_lo, int p_hi)
     return 0;
 }
 
-// Re-evaluate, on local planes [p_lo, p_hi), the sites whose stamp equals stamp_id.
+// Re-evaluate, on local planes [p_lo, p_hi), the sites whose stamp bit is set.
 // list: nloc int32; counter: one device unsigned int (zeroed by the caller).
-int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint8_t *stamp, uint32_t stamp_id, int32_t *list,
-                     unsigned int *counter)
+int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint32_t *stamp, int32_t *list, unsigned int *counter)
 {
     if (p_hi <= p_lo) return 0;
     if (int rc = nst_ensure(c)) return rc;
     if (int rc = rate_tables_ensure(c)) return rc;
     DirtyArgs d;
-    d.stamp = stamp; d.stamp_id = stamp_id; d.L = (int)c->n1; d.p_lo = p_lo; d.p_hi = p_hi;
+    d.stamp = stamp; d.s_lo = (int)(p_lo * c->plane); d.s_hi = (int)(p_hi * c->plane);
     d.list = list; d.n_list = counter;
-    const int nrows = (p_hi - p_lo) * (int)c->n1;
-    dirty_scan_kernel<<<(nrows + RB_WARPS - 1) / RB_WARPS, RB_WARPS * 32, 0, c->stream>>>(d);
+    const int n_words = ((d.s_hi + 31) >> 5) - (d.s_lo >> 5);
+    dirty_scan_kernel<<<(n_words + RB_WARPS * 32 - 1) / (RB_WARPS * 32), RB_WARPS * 32, 0, c->stream>>>(d);
     CET_CUDA(cudaGetLastError());
     const int64_t nsite = (int64_t)(p_hi - p_lo) * c->plane;
     const int grid = (int)std::min<int64_t>((nsite + RT_CHUNK * RT_WARPS - 1) / (RT_CHUNK * RT_WARPS), 148 * 5);

@@ -37,8 +37,7 @@ namespace cet {
 
 int thermal_cet_step(cet_ctx *c, const cet_thermal_params *p, const int32_t *stop_flag);
 int rates_rows(cet_ctx *c, int p_lo, int p_hi);                                  // rates.cu
-int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint8_t *stamp, uint32_t stamp_id, int32_t *lists,
-                     unsigned int *counters);
+int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint32_t *stamp, int32_t *list, unsigned int *counter);
 int comm_sweep_reduce(cet_ctx *c, double *plane_sum, int n, double *max_inout);   // comm.cu
 int comm_halo_exchange(cet_ctx *c, int fields);
 
@@ -347,27 +346,29 @@ struct ApplyArgs {
     const Record *records;
     unsigned int cap_fired;
     unsigned long long *claim;
-    uint8_t *stamp;
+    uint32_t *stamp;       // refresh requests, one bit per local site
     unsigned long long *nst;
     cet_rate_params P;
     int L, n0, i_off, np;
     int c_lo, c_hi;        // local planes with complete claims
     int own_lo, own_hi;    // local planes owned by this slab (for the counters)
     uint64_t seed;
-    uint32_t sweep, stamp_id;
+    uint32_t sweep;
     double defect_fraction;
 };
 
 // A site changed state: request a refresh of the site and of its neighbours.  The refresh pass
-// (rates.cu) re-evaluates every site whose stamp carries this sweep's id and rewrites its cached
-// neighbour-class word from a fresh gather — exactly the sites whose neighbourhood changed.
+// (rates.cu) re-evaluates every site whose stamp bit is set and rewrites its cached neighbour-class
+// word from a fresh gather — exactly the sites whose neighbourhood changed.  The stamps are a
+// bitmap (16.8 MB at 512^3: the ~1e7 scattered requests of a sweep are atomic ORs that meet in L2,
+// where one-byte stamps cost a 32-byte DRAM sector fill each).
 // (Maintaining the words here with one 64-bit atomic add per neighbour was measured: it removes the
 // gather from the refresh, -0.13 ms, but costs the apply kernel +0.52 ms per sweep at 6.6e5 events.)
 __device__ __forceinline__ void site_changed(const ApplyArgs &a, int site, int, int)
 {
     const int LL = a.L * a.L;
     const int p = site / LL, j = (site / a.L) % a.L, k = site % a.L;
-    a.stamp[site] = (uint8_t)a.stamp_id;
+    atomicOr(&a.stamp[site >> 5], 1u << (site & 31));
     const unsigned inb = inbounds_mask(a.i_off + p, j, k, a.n0, a.L);    // inside the GLOBAL lattice ...
 #pragma unroll 1
     for (int o = 0; o < 14; ++o) {
@@ -375,7 +376,7 @@ __device__ __forceinline__ void site_changed(const ApplyArgs &a, int site, int, 
         const int pn = p + c_nb_off[o][0];
         if (pn < 0 || pn >= a.np) continue;                             // ... and inside the local planes
         const int n = site + (c_nb_off[o][0] * a.L + c_nb_off[o][1]) * a.L + c_nb_off[o][2];
-        a.stamp[n] = (uint8_t)a.stamp_id;
+        atomicOr(&a.stamp[n >> 5], 1u << (n & 31));
     }
 }
 
@@ -470,8 +471,8 @@ static int sweep_alloc(cet_ctx *c)
         CET_CUDA(cudaMemsetAsync(c->claim, 0, (size_t)c->nloc * sizeof(unsigned long long), c->stream));
     }
     if (!c->stamp) {
-        CET_CUDA(cudaMalloc(&c->stamp, (size_t)c->nloc + 64));
-        CET_CUDA(cudaMemsetAsync(c->stamp, 0, (size_t)c->nloc + 64, c->stream));
+        CET_CUDA(cudaMalloc(&c->stamp, (size_t)c->nloc / 8 + 64));
+        CET_CUDA(cudaMemsetAsync(c->stamp, 0, (size_t)c->nloc / 8 + 64, c->stream));
     }
     if (!c->dirty) {
         c->cap_dirty = (size_t)c->nloc;               // occupied list + empty list, one entry per site each
@@ -594,10 +595,7 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
             if (int rc = rates_rows(c, R.eval_lo, R.eval_hi)) return rc;
             c->sweep_rates_valid = true;
         }
-        // one-byte stamps: ids cycle through 1..255, the array is cleared when the cycle restarts
-        const uint32_t stamp_id = (uint32_t)(c->stamp_cycle % 255) + 1;
-        if (stamp_id == 1) CET_CUDA(cudaMemsetAsync(c->stamp, 0, (size_t)c->nloc, c->stream));
-        c->stamp_cycle++;
+        CET_CUDA(cudaMemsetAsync(c->stamp, 0, (size_t)c->nloc / 8 + 8, c->stream));      // stamp bitmap of this sweep
         sweep_reset_kernel<<<1, 1, 0, c->stream>>>(c->sweep, max_slot);
         CET_CUDA(cudaMemsetAsync(c->plane_sum, 0, (size_t)c->n0 * sizeof(double), c->stream));
         {
@@ -635,7 +633,6 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
             b.P = c->rp; b.L = (int)c->n1; b.n0 = (int)c->n0; b.i_off = i_off; b.np = (int)c->np;
             b.c_lo = R.claim_lo; b.c_hi = R.claim_hi; b.own_lo = R.own_lo; b.own_hi = R.own_hi;
             b.seed = sp->seed; b.sweep = (uint32_t)c->sweep_index;
-            b.stamp_id = stamp_id;
             b.defect_fraction = sp->defect_fraction;
             ProfScope ps(c, PROF_APPLY);
             sweep_apply_kernel<<<148 * 32, 128, 0, c->stream>>>(b);
@@ -643,8 +640,7 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
         CET_CUDA(cudaGetLastError());
         {
             ProfScope ps(c, PROF_REFRESH);
-            if (int rc = rates_rows_dirty(c, R.eval_lo, R.eval_hi, c->stamp, stamp_id, c->dirty,
-                                          &c->sweep->n_dirty))
+            if (int rc = rates_rows_dirty(c, R.eval_lo, R.eval_hi, c->stamp, c->dirty, &c->sweep->n_dirty))
                 return rc;
         }
         // the totals are only needed for the next tau: reduce them here, next to the halo exchange, so
