@@ -370,12 +370,11 @@ __device__ __forceinline__ void site_changed(const ApplyArgs &a, int site, int, 
     const int p = site / LL, j = (site / a.L) % a.L, k = site % a.L;
     atomicOr(&a.stamp[site >> 5], 1u << (site & 31));
     const unsigned inb = inbounds_mask(a.i_off + p, j, k, a.n0, a.L);    // inside the GLOBAL lattice ...
-#pragma unroll 1
-    for (int o = 0; o < 14; ++o) {
-        if (!(inb >> o & 1u)) continue;
-        const int pn = p + c_nb_off[o][0];
-        if (pn < 0 || pn >= a.np) continue;                             // ... and inside the local planes
-        const int n = site + (c_nb_off[o][0] * a.L + c_nb_off[o][1]) * a.L + c_nb_off[o][2];
+#pragma unroll
+    for (int o = 0; o < 14; ++o) {                                       // unrolled: the offsets are immediates
+        const int pn = p + CET_NB_DI(o);
+        if (!(inb >> o & 1u) || pn < 0 || pn >= a.np) continue;          // ... and inside the local planes
+        const int n = site + (CET_NB_DI(o) * a.L + CET_NB_DJ(o)) * a.L + CET_NB_DK(o);
         atomicOr(&a.stamp[n >> 5], 1u << (n & 31));
     }
 }
