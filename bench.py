@@ -111,7 +111,7 @@ def cpu_rate_sample(threads):
         O.site_rates(st, th, ph, T, df, Ls, p)
         reps += 1
         dt = time.perf_counter() - t0
-        if dt > 10.0 or reps >= 50:
+        if dt > 10.0 or reps >= 400:                 # ~10 s of host work (bounded sample)
             break
     return Ls ** 3 * reps / dt, dt, reps
 
