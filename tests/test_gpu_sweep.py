@@ -93,7 +93,8 @@ def test_diffusion_only_conserves_atoms(cet):
 def test_level3_observables_vs_serial_oracle(cet, oracle):
     """Level-3 parity: over N seeds, the sublattice path and the serial oracle, run to the same
     number of executed events from the same initial lattice, agree on occupied fraction, grain
-    count, Re fraction and equiaxed fraction within 4 standard errors + 3 % of the mean."""
+    count, Re fraction, equiaxed fraction and mean grain aspect ratio within 4 standard errors + 3 %
+    of the mean."""
     from cetkmc import _host
     from cetkmc._config import rate_params
     L, n_events, n_seeds, c = 16, 1500, 6, 0.1
@@ -110,7 +111,7 @@ def test_level3_observables_vs_serial_oracle(cet, oracle):
         assert r["steps_done"] == n_events
         m = _host.compute_metrics(o[0], o[2], o[3])
         obs_o.append([(o[0] != 0).sum(), m["GrainCount"], (o[0] == 2).sum() / max((o[0] != 0).sum(), 1),
-                      m["EquiaxedFraction"]])
+                      m["EquiaxedFraction"], m["AspectRatio"]])
         ctx = cet.Context(L=L)
         ctx.set_rate_params(rate_params(c))
         ctx.upload(state=st, theta=th, phi=ph, T=T, defects=df)
@@ -123,7 +124,7 @@ def test_level3_observables_vs_serial_oracle(cet, oracle):
         m = _host.compute_metrics(f["state"], f["theta"], f["phi"])
         scale = n_events / applied                   # the last sweep overshoots by a few events
         obs_g.append([(f["state"] != 0).sum() * scale, m["GrainCount"] * scale,
-                      (f["state"] == 2).sum() / max((f["state"] != 0).sum(), 1), m["EquiaxedFraction"]])
+                      (f["state"] == 2).sum() / max((f["state"] != 0).sum(), 1), m["EquiaxedFraction"], m["AspectRatio"]])
     obs_o, obs_g = np.array(obs_o, dtype=float), np.array(obs_g, dtype=float)
     mo, mg = obs_o.mean(0), obs_g.mean(0)
     se = np.sqrt(obs_o.var(0, ddof=1) / n_seeds + obs_g.var(0, ddof=1) / n_seeds)
