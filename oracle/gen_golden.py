@@ -7,7 +7,8 @@ code on seeded inputs:
     thermal_*.npz     update_temperature_cet / update_temperature (thermal_solver.py:36,107)
     traj_*.npz        run_kmc (kmc_simulation.py:203) final arrays + metrics.csv rows
     grains_*.npz      utils.get_clusters / metrics.compute_metrics (utils.py:69, metrics.py:41)
-Usage:  python oracle/gen_golden.py [--grains-only]
+    defects_*.npz     defects.introduce_defects (defects.py:25)
+Usage:  python oracle/gen_golden.py [--grains-only | --defects-only]
 """
 import io
 import os
@@ -72,11 +73,33 @@ def grains_cases(ref):
         print(f"grains_{name}: L={L} grains={len(clusters)} AR={m['AspectRatio']:.4f} eq={m['EquiaxedFraction']:.3f}")
 
 
+def defects_cases(ref):
+    """defects.introduce_defects (defects.py:25-31) with NumPy's global stream seeded."""
+    de = ref["defects"]
+    for name, L, seed in (("c20", 14, 4), ("c35", 20, 9)):
+        rng = np.random.default_rng(seed)
+        st = rng.choice(np.array([0, 1, 2, 3, 4]), size=(L, L, L), p=[.3, .25, .1, .3, .05]).astype(np.int64)
+        T = 2500 + 1500 * rng.random((L, L, L))
+        T[rng.random((L, L, L)) < 0.03] = -5.0                     # defects.py:13: falls back to T_SUB
+        np.random.seed(seed)
+        mask, density = de.introduce_defects(st.copy(), st, T, apply_to_state=False)
+        nxt = np.random.random()                                     # stream position after the call
+        np.random.seed(seed)
+        mask_noT, _ = de.introduce_defects(st.copy(), st, None)
+        np.savez_compressed(os.path.join(OUT, f"defects_{name}.npz"), state=st.astype(np.int8), T=T, seed=np.int64(seed),
+                            mask=mask.astype(np.int8), density=np.float64(density), next_draw=np.float64(nxt),
+                            mask_noT=mask_noT.astype(np.int8))
+        print(f"defects_{name}: L={L} carbon={(st == 3).sum()} masked={mask.sum()} / {mask_noT.sum()} (no T)")
+
+
 def main():
     ref = refharness.load()
     os.makedirs(OUT, exist_ok=True)
     if "--grains-only" in sys.argv:
         grains_cases(ref)
+        return
+    if "--defects-only" in sys.argv:
+        defects_cases(ref)
         return
     li, ts, km = ref["lattice_init"], ref["thermal_solver"], ref["kmc_simulation"]
 
@@ -121,6 +144,7 @@ def main():
     print("thermal fixtures written")
 
     grains_cases(ref)
+    defects_cases(ref)
 
     # ---- trajectories ------------------------------------------------------------------------
     import pandas as pd

@@ -77,3 +77,19 @@ def test_defects_philox_mode(cet):
     p = 0.12 * np.exp(-0.3 / (8.617333262e-5 * 3000.0))
     n_c = int((st == 3).sum())
     assert abs(m1.sum() - p * n_c) < 5 * np.sqrt(p * (1 - p) * n_c)
+
+
+@pytest.mark.parametrize("name", ["defects_c20.npz", "defects_c35.npz"])
+def test_defects_dropin_golden(cet, name):
+    """cetkmc.defects.introduce_defects against the reference's own output (tests/golden/defects_*.npz)."""
+    from conftest import golden
+    from cetkmc import defects as D
+    g = golden(name)
+    st, T, seed = g["state"].astype(np.int64), g["T"], int(g["seed"])
+    np.random.seed(seed)
+    mask, density = D.introduce_defects(st.copy(), st, T, apply_to_state=False)
+    np.testing.assert_array_equal(mask, g["mask"])
+    assert density == float(g["density"]) and np.random.random() == float(g["next_draw"])
+    np.random.seed(seed)
+    mask_noT, _ = D.introduce_defects(st.copy(), st, None)
+    np.testing.assert_array_equal(mask_noT, g["mask_noT"])

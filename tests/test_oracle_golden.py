@@ -89,3 +89,16 @@ def test_grain_clustering_golden(oracle, name):
     for k in ("AspectRatio", "EquiaxedFraction", "NucleationDensity", "AvgGrainSize", "GrainCount", "DefectDensity",
               "Grain_d50_um", "Grain_d90_um"):
         assert m[k] == g[f"m_{k}"], k
+
+
+@pytest.mark.parametrize("name", ["defects_c20.npz", "defects_c35.npz"])
+def test_defect_mask_golden(oracle, name):
+    """defects.py:4-31 restatement against the reference's own masks (NumPy global stream seeded)."""
+    g = golden(name)
+    st, T, seed = g["state"].astype(np.int64), g["T"], int(g["seed"])
+    rs = np.random.RandomState(seed)
+    np.testing.assert_array_equal(oracle.track_defects(st, T, rs), g["mask"])
+    assert rs.random_sample() == float(g["next_draw"])                    # one draw per carbon site, no more
+    assert g["mask"].sum() / (g["mask"].size * (5e-6) ** 3) == float(g["density"])
+    u = np.random.RandomState(seed).random_sample(int((st == 3).sum()))
+    np.testing.assert_array_equal(g["mask_noT"][st == 3], (u < 0.12).astype(np.int8))      # T=None: flat probability

@@ -53,3 +53,26 @@ def test_helpers_live(oracle, ref):
     for _ in range(20):
         a = rng.uniform(0, np.pi, 2); b = rng.uniform(0, 2 * np.pi, 2)
         assert oracle.misorientation(a[0], b[0], a[1], b[1]) == ker.compute_misorientation(a[0], b[0], a[1], b[1])
+
+
+def test_clusters_and_metrics_live(oracle, ref):
+    """utils.get_clusters / metrics.compute_metrics (utils.py:69, metrics.py:41) vs the restatement."""
+    st, th, ph = oracle.grown_lattice(11, seed=5, grain=4, fill=0.6, jitter=0.25)
+    clusters, visited = ref["utils"].get_clusters(st, th, ph, theta_threshold=0.5)
+    o_clusters, o_visited = oracle.get_clusters(st, th, ph, 0.5)
+    np.testing.assert_array_equal(np.asarray(visited), o_visited)
+    assert [sorted(c) for c in clusters] == [sorted(c) for c in o_clusters]
+    m, om = ref["metrics"].compute_metrics(st, th, ph), oracle.compute_metrics(st, th, ph)
+    for k in ("AspectRatio", "EquiaxedFraction", "NucleationDensity", "AvgGrainSize", "GrainCount", "Grain_d50_um", "Grain_d90_um"):
+        assert m[k] == om[k], k
+
+
+def test_defects_live(oracle, ref):
+    rng = np.random.default_rng(2)
+    st = rng.choice(np.array([0, 1, 2, 3]), size=(9, 9, 9), p=[.3, .3, .1, .3]).astype(np.int64)
+    T = 2600 + 1200 * rng.random(st.shape); T[0, 0, :3] = 0.0
+    np.random.seed(8)
+    mask, _ = ref["defects"].introduce_defects(st.copy(), st, T)
+    rs = np.random.RandomState(8)
+    np.testing.assert_array_equal(mask, oracle.track_defects(st, T, rs))
+    assert np.random.random() == rs.random_sample()
