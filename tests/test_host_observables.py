@@ -77,3 +77,35 @@ def test_snapshot_round_trip_and_rng_json(tmp_path):
     assert np.array_equal(np.random.random(5), want)
     G, R, R_phys, gr = campaign._gr(30, 2800, 2e13)                                        # kmc_simulation.py:236-239
     assert G == (3695 - 2800) / (30 * 5e-6) and R == 2e13 * 2.74e-10 / 5e-6 and gr == G / R_phys
+
+
+def test_gr_sweep_partitions_cases_over_ranks_and_merges(tmp_path, monkeypatch):
+    """Config 5 is replicas only: case q belongs to rank q % world; the per-rank maps merge into one
+    cet_map.csv ordered by case.  The GPU run of a case is stubbed (host logic only)."""
+    import csv
+    from cetkmc import campaign
+    monkeypatch.chdir(tmp_path)
+    calls = []
+
+    def fake_run(L, n_sweeps, temp, nu_dep, output_prefix, device, **kw):
+        calls.append((temp, nu_dep, device))
+        os.makedirs(f"outputs/{output_prefix}", exist_ok=True)
+        with open(f"outputs/{output_prefix}/metrics.csv", "w", newline="") as fh:
+            w = csv.DictWriter(fh, fieldnames=["Step", "Time", "AspectRatio", "EquiaxedFraction", "GrainCount", "AvgGrainSize",
+                                               "NucleationCount", "CET_Class", "CET_Detected"])
+            w.writeheader()
+            w.writerow(dict(Step=n_sweeps - 1, Time=1e-9, AspectRatio=temp / 1000, EquiaxedFraction=0.5, GrainCount=7,
+                            AvgGrainSize=1.0, NucleationCount=3, CET_Class="Columnar", CET_Detected=False))
+
+    monkeypatch.setattr(campaign, "run_cet_sublattice", fake_run)
+    temps, rates = [2600, 2800, 3000], [2e12, 2e13]
+    r0 = campaign.run_gr_sweep(temps, rates, L=8, n_sweeps=5, rank=0, world=2, devices=[0])
+    r1 = campaign.run_gr_sweep(temps, rates, L=8, n_sweeps=5, rank=1, world=2, devices=[1])
+    assert [r["case"] for r in r0] == [0, 2, 4] and [r["case"] for r in r1] == [1, 3, 5]
+    assert len(calls) == 6 and {c[2] for c in calls[:3]} == {0} and {c[2] for c in calls[3:]} == {1}
+    merged = campaign.merge_cet_map()
+    assert [int(r["case"]) for r in merged] == list(range(6))
+    assert [float(r["T_sub"]) for r in merged] == [2600, 2600, 2800, 2800, 3000, 3000]
+    G = (3695 - 2600) / (8 * 5e-6)
+    assert float(merged[0]["G"]) == G and float(merged[0]["G_over_R"]) == G / (2e12 * 2.74e-10 / 5e-6)
+    assert os.path.exists("outputs/gr_sweep/cet_map.csv")
