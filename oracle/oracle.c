@@ -439,3 +439,61 @@ int64_t oracle_kmc_run(int64_t *state, int64_t *atom_type, double *theta, double
     free(ty); free(po); free(ra); free(ta); free(at); free(Tn);
     return done;
 }
+
+/* ---------------------------------------------------------------------------------------
+ * Grain clustering (utils.py:28-84): DFS with an explicit stack over the 14-offset
+ * neighbourhood, joining occupied sites whose misorientation (kmc_event_rates.py:10-23) is
+ * below theta_threshold.  Cubic lattice (L, L, L).  visited[s] receives the cluster number
+ * 1.. in discovery (raster) order, 0 on empty sites; sizes[q] / box_lo / box_hi [3q+axis]
+ * describe cluster q+1 (sizes may be NULL).  Returns the number of clusters; cap bounds the
+ * per-cluster outputs.
+ * --------------------------------------------------------------------------------------- */
+int64_t oracle_clusters(const int64_t *state, const double *theta, const double *phi, int64_t L,
+                        double theta_threshold, int32_t *visited, int64_t cap, int32_t *sizes,
+                        int32_t *box_lo, int32_t *box_hi)
+{
+    const int64_t N = L * L * L;
+    int64_t *stack = (int64_t *)malloc((size_t)(N > 0 ? N : 1) * sizeof(int64_t));
+    int64_t label = 0;
+    for (int64_t s = 0; s < N; ++s) visited[s] = 0;
+    for (int64_t s0 = 0; s0 < N; ++s0) {                              /* utils.py:35-38 raster scan */
+        if (state[s0] == 0 || visited[s0] != 0) continue;
+        ++label;
+        int64_t top = 0, size = 1;
+        int32_t lo[3] = {(int32_t)(s0 / (L * L)), (int32_t)((s0 / L) % L), (int32_t)(s0 % L)};
+        int32_t hi[3] = {lo[0], lo[1], lo[2]};
+        stack[top++] = s0;
+        visited[s0] = (int32_t)label;
+        while (top > 0) {                                              /* :44-63 */
+            const int64_t c = stack[--top];
+            const int64_t ci = c / (L * L), cj = (c / L) % L, ck = c % L;
+            int64_t nb[14 * 3];
+            const int n = oracle_bcc_neighbors(ci, cj, ck, L, nb);
+            for (int q = 0; q < n; ++q) {
+                const int64_t t = (nb[3 * q] * L + nb[3 * q + 1]) * L + nb[3 * q + 2];
+                if (state[t] == 0 || visited[t] != 0) continue;
+                const double mis = phi ? oracle_misorientation(theta[c], phi[c], theta[t], phi[t])
+                                       : fabs(theta[c] - theta[t]);
+                if (mis < theta_threshold) {
+                    visited[t] = (int32_t)label;
+                    stack[top++] = t;
+                    ++size;
+                    for (int ax = 0; ax < 3; ++ax) {
+                        const int32_t v = (int32_t)nb[3 * q + ax];
+                        if (v < lo[ax]) lo[ax] = v;
+                        if (v > hi[ax]) hi[ax] = v;
+                    }
+                }
+            }
+        }
+        if (label <= cap) {
+            if (sizes) sizes[label - 1] = (int32_t)size;
+            for (int ax = 0; ax < 3; ++ax) {
+                if (box_lo) box_lo[3 * (label - 1) + ax] = lo[ax];
+                if (box_hi) box_hi[3 * (label - 1) + ax] = hi[ax];
+            }
+        }
+    }
+    free(stack);
+    return label;
+}

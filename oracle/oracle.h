@@ -54,6 +54,9 @@ int64_t oracle_kmc_run(int64_t *state, int64_t *atom_type, double *theta, double
                        double *total_time, int64_t *nucleation_count, int *terminated,
                        uint8_t *log_type, int64_t *log_pos, int64_t *log_target,
                        int32_t *log_atom, double *log_rate, double *log_total);
+int64_t oracle_clusters(const int64_t *state, const double *theta, const double *phi, int64_t L,
+                        double theta_threshold, int32_t *visited, int64_t cap, int32_t *sizes,
+                        int32_t *box_lo, int32_t *box_hi);
 #ifdef __cplusplus
 }
 #endif

@@ -146,6 +146,8 @@ def lib():
                                  vp, ip, vp, ip, vp, ip, dp, ip, C.POINTER(C.c_int),
                                  vp, vp, vp, vp, vp, vp]
     L.oracle_kmc_run.restype = C.c_int64
+    L.oracle_clusters.argtypes = [vp, vp, vp, C.c_int64, C.c_double, vp, C.c_int64, vp, vp, vp]
+    L.oracle_clusters.restype = C.c_int64
     _lib = L
     return L
 
@@ -467,6 +469,21 @@ def get_clusters(state, theta, phi=None, theta_threshold=0.5):
                 clusters.append(cluster)
                 label += 1
     return clusters, np.array(vis, dtype=np.int32).reshape(state.shape)
+
+
+def clusters_fast(state, theta, phi=None, theta_threshold=0.5):
+    """utils.py:28-84 in C (oracle.c: oracle_clusters) for lattices the pure-Python DFS above is too
+    slow for.  Returns dict(n, visited, size, box_lo, box_hi) with clusters in discovery order."""
+    L = state.shape[0]
+    assert state.shape == (L, L, L)
+    st, th = _i64(state), _f64(theta)
+    ph = None if phi is None else _f64(phi)
+    visited = np.zeros(state.shape, np.int32)
+    cap = int(np.count_nonzero(st))
+    size = np.zeros(max(cap, 1), np.int32); lo = np.zeros((max(cap, 1), 3), np.int32); hi = np.zeros((max(cap, 1), 3), np.int32)
+    n = lib().oracle_clusters(_ptr(st), _ptr(th), _ptr(ph), L, float(theta_threshold), _ptr(visited), cap,
+                              _ptr(size), _ptr(lo), _ptr(hi))
+    return dict(n=int(n), visited=visited, size=size[:n], box_lo=lo[:n], box_hi=hi[:n])
 
 
 def calculate_aspect_ratio(cluster):

@@ -102,3 +102,14 @@ def test_defect_mask_golden(oracle, name):
     assert g["mask"].sum() / (g["mask"].size * (5e-6) ** 3) == float(g["density"])
     u = np.random.RandomState(seed).random_sample(int((st == 3).sum()))
     np.testing.assert_array_equal(g["mask_noT"][st == 3], (u < 0.12).astype(np.int8))      # T=None: flat probability
+
+
+@pytest.mark.parametrize("name", ["grains_grown12.npz", "grains_grown16.npz", "grains_half14.npz"])
+def test_grain_clustering_c_restatement_golden(oracle, name):
+    """oracle.c's DFS (used for lattices the pure-Python one is too slow for) against the reference."""
+    g = golden(name)
+    f = oracle.clusters_fast(g["state"].astype(np.int64), g["theta"], g["phi"], 0.5)
+    np.testing.assert_array_equal(f["visited"], g["visited"])
+    np.testing.assert_array_equal(f["size"], g["sizes"])
+    dims = f["box_hi"] - f["box_lo"] + 1
+    np.testing.assert_array_equal(dims.max(1) / np.maximum(dims.min(1), 1), g["aspect"])
