@@ -20,7 +20,9 @@
 // Warps are autonomous inside a tile (only __syncwarp): a persistent CTA loads the tables once and
 // pulls 2048-site chunks from a global queue (rate_cta_loop).
 #pragma once
+#if defined(__CUDACC__)
 #include "reduce.cuh"
+#endif
 #include "site_rates.cuh"
 
 namespace cet {

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <vector>
 #include "../../cet-driven-simulation-for-3d-printing-am-kmc-approach_b200/csrc/site_rates.cuh"
+#include "../../cet-driven-simulation-for-3d-printing-am-kmc-approach_b200/csrc/rate_tile.cuh"
 
 using namespace cet;
 
@@ -40,4 +41,17 @@ extern "C" long long hostsim_events(const uint8_t *vox, const double *theta, con
                 }
     }
     return n;
+}
+
+// The cached neighbour-class word of every site (rate_tile.cuh: nb_code_lut, nst_word) — what
+// nst_build_kernel and the refresh write — so that its encoding can be checked without a GPU.
+extern "C" void hostsim_nst_words(const uint8_t *vox, int L, const cet_rate_params *P, uint64_t *out)
+{
+    const uint64_t lut = nb_code_lut(*P);
+    for (int i = 0; i < L; ++i)
+        for (int j = 0; j < L; ++j)
+            for (int k = 0; k < L; ++k) {
+                const long long s = ((long long)i * L + j) * L + k;
+                out[s] = nst_word(lut, vox, s, i, j, k, L, L);
+            }
 }

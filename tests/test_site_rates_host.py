@@ -47,3 +47,29 @@ def test_site_events_match_reference(hostsim, name):
     nondep = g["ev_type"] != 0                      # species of dep events come from the draw stream
     np.testing.assert_array_equal(atom[:n][nondep], g["ev_atom"][nondep])
     np.testing.assert_allclose(rate[:n], g["ev_rate"], rtol=1e-13, atol=0.0)
+
+
+def test_neighbour_class_words(hostsim):
+    """The cache word the dense kernel decodes with shifts and ANDs (rate_tile.cuh): nibble o of a
+    site = class of neighbour o — bit 0 occupied, bit 1 Re, bit 2 C, bit 3 attachable species, 8
+    alone = outside the lattice — and bits 56 / 57 flag k == 0 / k == L-1."""
+    from cetkmc._config import rate_params
+    L = 7
+    rng = np.random.default_rng(4)
+    st = rng.integers(0, 6, (L, L, L)).astype(np.uint8)            # 0 empty, 1 W, 2 Re, 3 C, 4 defect, 5 unknown species
+    vox = (st | (rng.integers(0, 2, (L, L, L)).astype(np.uint8) << 4)).ravel()
+    P = rate_params(0.1)
+    out = np.zeros(L ** 3, np.uint64)
+    hostsim.hostsim_nst_words(vox.ctypes.data_as(C.c_void_p), L, C.byref(P), out.ctypes.data_as(C.c_void_p))
+    code = {0: 0, 1: 8 | 1, 2: 8 | 2 | 1, 3: 8 | 4 | 1, 4: 1, 5: 1}
+    offs = [(1, 1, 0), (1, -1, 0), (-1, 1, 0), (-1, -1, 0), (0, 1, 1), (0, 1, -1), (0, -1, 1), (0, -1, -1),
+            (2, 0, 0), (-2, 0, 0), (0, 2, 0), (0, -2, 0), (0, 0, 2), (0, 0, -2)]       # kmc_event_rates.py:29-36
+    for i in range(L):
+        for j in range(L):
+            for k in range(L):
+                w = (1 << 56 if k == 0 else 0) | (1 << 57 if k == L - 1 else 0)
+                for o, (di, dj, dk) in enumerate(offs):
+                    ni, nj, nk = i + di, j + dj, k + dk
+                    inb = 0 <= ni < L and 0 <= nj < L and 0 <= nk < L
+                    w |= (code[int(st[ni, nj, nk])] if inb else 8) << (4 * o)
+                assert int(out[(i * L + j) * L + k]) == w, (i, j, k)
