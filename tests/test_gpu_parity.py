@@ -172,8 +172,10 @@ def test_site_rates_dense_interfaces(cet, oracle, L):
     assert ctx.events_count()[0] == ev["rate"].size
 
 
+# the last case is BASELINE.json configs[1]: the 128^3 lattice with injected draws (few steps: the
+# oracle rebuilds all 2.1e6 rates for every executed event, ~0.5 s per step)
 @pytest.mark.parametrize("L,steps,defect_fraction,c,ups", [(12, 400, 0.02, 0.1, 0), (16, 300, 0.0, 0.0, 2),
-                                                              (20, 250, 3e-3, 0.2, 30)])
+                                                              (20, 250, 3e-3, 0.2, 30), (128, 16, 3e-3, 0.1, 0)])
 def test_kmc_run_bit_exact_vs_oracle(cet, oracle, L, steps, defect_fraction, c, ups):
     from cetkmc._config import rate_params, thermal_params
     st, th, ph, T, df = oracle.half_grown_lattice(L, seed=100 + L, T_updates=ups, grain=4)
