@@ -41,7 +41,7 @@ struct SweepState {
     unsigned long long n_fired_total, n_applied, n_nuc;   // running totals over owned sites (device atomics)
     unsigned long long n_refreshed_total;                 // sites re-evaluated by the neighbour-rate refresh
     unsigned int n_fired;                           // fired-site list length of the current sweep
-    unsigned int n_dirty, n_dirty_emp;              // refresh lists (occupied, empty) — adjacent: one pointer
+    unsigned int n_dirty, n_dirty_emp;              // refresh list length (one mixed list; n_dirty_emp stays 0, kept for the layout)
     unsigned int overflow, dirty_overflow, pad0_;   // the fired list overflowed (events dropped)
     double sum_rate, max_rate;                      // totals of the rates seen by the last sweep
     double tau, time;                               // interval of the next sweep; accumulated time
