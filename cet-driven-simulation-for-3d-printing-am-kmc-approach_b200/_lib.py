@@ -112,6 +112,7 @@ SIGNATURES = {
     "cet_grains_stats": [_VP, _I64, _VP, _VP, _VP, _VP],
     "cet_grains_download_labels": [_VP, _VP],
     "cet_debug_nst_mismatches": [_VP, C.POINTER(_I64)],
+    "cet_debug_flags": [_VP, C.c_int],
     "cet_profile_enable": [_VP, C.c_int],
     "cet_profile_read": [_VP, C.c_int, C.POINTER(_F64), C.POINTER(_I64), C.c_int],
     "cet_timer_begin": [_VP],
@@ -429,6 +430,11 @@ class Context:
         n = C.c_int64(0)
         check(lib().cet_debug_nst_mismatches(self._h, C.byref(n)), "cet_debug_nst_mismatches")
         return n.value
+
+    def debug_flags(self, flags):
+        """Kernel selection of sweep_run (tests / profiling): 1 = tiles staged without TMA, 2 = the
+        gather kernels of the first design instead of the fused tile kernel."""
+        check(lib().cet_debug_flags(self._h, int(flags)), "cet_debug_flags")
 
     def sweep_state(self):
         """(sweep_index, tau, time) of the sweep clock — see sweep_set_state."""

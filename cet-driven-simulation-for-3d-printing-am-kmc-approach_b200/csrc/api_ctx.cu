@@ -99,10 +99,10 @@ __global__ void nst_check_kernel(const uint64_t lut, const uint8_t *__restrict__
     }
 }
 
-static int grid_for(int64_t n, int block)
+static int grid_for(cet_ctx *c, int64_t n, int block)
 {
     int64_t g = (n + block - 1) / block;
-    const int64_t cap = 148 * 16;
+    const int64_t cap = (int64_t)sm_count(c) * 16;
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -110,7 +110,7 @@ int nst_build(cet_ctx *c, int p_lo, int p_hi)
 {
     if (p_hi <= p_lo) return 0;
     const int64_t n = (int64_t)(p_hi - p_lo) * c->plane;
-    nst_build_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(nb_code_lut(c->rp), c->vox, c->nst, (int)c->n1, (int)c->n0,
+    nst_build_kernel<<<grid_for(c, n, 256), 256, 0, c->stream>>>(nb_code_lut(c->rp), c->vox, c->nst, (int)c->n1, (int)c->n0,
                                                                (int)(c->i_begin - c->halo), p_lo, p_hi);
     CET_CUDA(cudaGetLastError());
     return 0;
@@ -132,7 +132,7 @@ int orient_update(cet_ctx *c, int64_t p_lo, int64_t p_hi)
 {
     if (p_hi <= p_lo) return 0;
     const int64_t off = p_lo * c->plane, n = (p_hi - p_lo) * c->plane;
-    orient_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->theta + off, c->phi + off, c->v + off, n);
+    orient_kernel<<<grid_for(c, n, 256), 256, 0, c->stream>>>(c->theta + off, c->phi + off, c->v + off, n);
     CET_CUDA(cudaGetLastError());
     return 0;
 }
@@ -261,7 +261,7 @@ int cet_destroy(cet_ctx *c)
                     c->row_occ, c->row_emp, c->row_dep, c->row_depcnt, c->seg, c->total, c->q_top,
                     c->stage, c->kmc, c->d_py, c->d_np, c->d_sp, c->d_log, c->sweep, c->claim,
                     c->records, c->blk_sum, c->blk_max, c->plane_sum, c->stamp, c->dirty, c->fired,
-                    c->grain_label, c->grain_gid, c->rate_tab};
+                    c->grain_label, c->grain_gid, c->rate_tab, c->cvox, c->pairop, c->tile_flag};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &sp : c->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -294,7 +294,7 @@ int cet_set_rate_params(cet_ctx *c, const cet_rate_params *p)
     c->have_rp = true;
     c->rate_tab_valid = false;
     c->nst_valid = false;             // the cached neighbour classes depend on the state ids
-    c->rates_valid = false; c->sweep_rates_valid = false;
+    lattice_changed(c);
     return 0;
 }
 
@@ -307,6 +307,9 @@ int cet_upload(cet_ctx *c, const int64_t *state, const double *theta, const doub
     const int64_t off = c->owned_offset();
     const size_t fb = (size_t)n * sizeof(double);
     if ((theta || phi) && !c->cubic) { set_error("cet_upload: theta/phi need a cubic context"); return 1; }
+    // everything derived from the lattice is stale from here on, also when the call fails half way
+    lattice_changed(c);
+    if (state) c->nst_valid = false;
     if (theta) CET_CUDA(cudaMemcpyAsync(c->theta + off, theta, fb, cudaMemcpyHostToDevice, c->stream));
     if (phi) CET_CUDA(cudaMemcpyAsync(c->phi + off, phi, fb, cudaMemcpyHostToDevice, c->stream));
     if (T) { CET_CUDA(cudaMemcpyAsync(c->T + off, T, fb, cudaMemcpyHostToDevice, c->stream)); c->T_finite = false; }
@@ -319,7 +322,7 @@ int cet_upload(cet_ctx *c, const int64_t *state, const double *theta, const doub
         CET_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), c->stream));
         if (state) { ds = (int64_t *)p; p += (size_t)n * 8; CET_CUDA(cudaMemcpyAsync(ds, state, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream)); }
         if (defects) { dd = (int64_t *)p; CET_CUDA(cudaMemcpyAsync(dd, defects, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream)); }
-        pack_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(ds, dd, c->vox + off, n, bad);
+        pack_kernel<<<grid_for(c, n, 256), 256, 0, c->stream>>>(ds, dd, c->vox + off, n, bad);
         CET_CUDA(cudaGetLastError());
         if (state) c->nst_valid = false;
         int hbad = 0;
@@ -330,7 +333,6 @@ int cet_upload(cet_ctx *c, const int64_t *state, const double *theta, const doub
     }
     if (theta || phi) if (int rc = orient_update(c, c->halo, c->np - c->halo)) return rc;
     CET_CUDA(cudaStreamSynchronize(c->stream));
-    c->rates_valid = false; c->sweep_rates_valid = false;
     return 0;
 }
 
@@ -347,7 +349,7 @@ int cet_download(cet_ctx *c, int64_t *state, int64_t *atom_type, double *theta, 
     if (T) CET_CUDA(cudaMemcpyAsync(T, c->T + off, fb, cudaMemcpyDeviceToHost, c->stream));
     if (state || atom_type) {
         if (int rc = ensure_stage(c, (size_t)n * 8)) return rc;
-        unpack_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->vox + off, (int64_t *)c->stage, n);
+        unpack_kernel<<<grid_for(c, n, 256), 256, 0, c->stream>>>(c->vox + off, (int64_t *)c->stage, n);
         CET_CUDA(cudaGetLastError());
         // kmc_simulation.py:281-282,293-294,306-307,314-315,324-325: atom_type is written with
         // the same value as state at every update, so one unpack serves both arrays.
@@ -373,7 +375,7 @@ int cet_upload_prev_state(cet_ctx *c, const int64_t *prev_state)
     int64_t *ds = (int64_t *)((char *)c->stage + 256);
     CET_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), c->stream));
     CET_CUDA(cudaMemcpyAsync(ds, prev_state, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
-    pack_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(ds, nullptr, c->vox_prev + off, n, bad);
+    pack_kernel<<<grid_for(c, n, 256), 256, 0, c->stream>>>(ds, nullptr, c->vox_prev + off, n, bad);
     CET_CUDA(cudaGetLastError());
     int hbad = 0;
     CET_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -398,8 +400,8 @@ int cet_upload_packed(cet_ctx *c, const uint8_t *packed)
     CET_CUDA(cudaMemcpyAsync(c->vox + c->owned_offset(), packed, (size_t)c->owned_sites(),
                              cudaMemcpyHostToDevice, c->stream));
     c->nst_valid = false;
+    lattice_changed(c);
     CET_CUDA(cudaStreamSynchronize(c->stream));
-    c->rates_valid = false; c->sweep_rates_valid = false;
     return 0;
 }
 
@@ -440,7 +442,7 @@ int cet_counts(cet_ctx *c, int64_t counts[16])
     if (int rc = ensure_stage(c, 16 * sizeof(unsigned long long))) return rc;
     CET_CUDA(cudaMemsetAsync(c->stage, 0, 16 * sizeof(unsigned long long), c->stream));
     const int64_t n = c->owned_sites();
-    counts_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->vox + c->owned_offset(), n,
+    counts_kernel<<<grid_for(c, n, 256), 256, 0, c->stream>>>(c->vox + c->owned_offset(), n,
                                                            (unsigned long long *)c->stage);
     CET_CUDA(cudaGetLastError());
     unsigned long long h[16];
@@ -461,13 +463,20 @@ int cet_debug_nst_mismatches(cet_ctx *c, int64_t *n_bad)
     if (int rc = ensure_stage(c, 8)) return rc;
     CET_CUDA(cudaMemsetAsync(c->stage, 0, 8, c->stream));
     const int64_t n = (int64_t)(hi - lo) * c->plane;
-    nst_check_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(nb_code_lut(c->rp), c->vox, c->nst, (int)c->n1, (int)c->n0, i_off, lo, hi,
+    nst_check_kernel<<<grid_for(c, n, 256), 256, 0, c->stream>>>(nb_code_lut(c->rp), c->vox, c->nst, (int)c->n1, (int)c->n0, i_off, lo, hi,
                                                                (unsigned long long *)c->stage);
     CET_CUDA(cudaGetLastError());
     unsigned long long h = 0;
     CET_CUDA(cudaMemcpyAsync(&h, c->stage, 8, cudaMemcpyDeviceToHost, c->stream));
     CET_CUDA(cudaStreamSynchronize(c->stream));
     *n_bad = (int64_t)h;
+    return 0;
+}
+
+int cet_debug_flags(cet_ctx *c, int flags)
+{
+    CET_REQUIRE(c, "cet_debug_flags: NULL ctx");
+    c->debug_flags = flags;
     return 0;
 }
 

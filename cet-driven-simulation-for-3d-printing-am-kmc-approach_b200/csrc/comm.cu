@@ -84,21 +84,23 @@ int comm_halo_exchange(cet_ctx *c, int fields)
     if (fields & 2) { fl[nf++] = {(char *)c->theta, 8}; fl[nf++] = {(char *)c->phi, 8}; }
     if (fields & 4) fl[nf++] = {(char *)c->T, 8};
     CET_NCCL(g_nccl.GroupStart());
+    ncclResult_t first = ncclSuccess;    // an early return would leave the group open: remember the first error, always close
+    auto op = [&](ncclResult_t r) { if (first == ncclSuccess) first = r; };
     for (int f = 0; f < nf; ++f) {
         const size_t bytes = n * fl[f].esz;
         char *b = fl[f].base;
         if (lower >= 0) {
-            CET_NCCL(g_nccl.Send(b + (size_t)H * c->plane * fl[f].esz, bytes, ncclChar, lower, comm, c->stream));
-            CET_NCCL(g_nccl.Recv(b, bytes, ncclChar, lower, comm, c->stream));
+            op(g_nccl.Send(b + (size_t)H * c->plane * fl[f].esz, bytes, ncclChar, lower, comm, c->stream));
+            op(g_nccl.Recv(b, bytes, ncclChar, lower, comm, c->stream));
         }
         if (upper < c->world) {
-            CET_NCCL(g_nccl.Send(b + (size_t)(c->np - 2 * H) * c->plane * fl[f].esz, bytes, ncclChar, upper, comm,
-                                 c->stream));
-            CET_NCCL(g_nccl.Recv(b + (size_t)(c->np - H) * c->plane * fl[f].esz, bytes, ncclChar, upper, comm,
-                                 c->stream));
+            op(g_nccl.Send(b + (size_t)(c->np - 2 * H) * c->plane * fl[f].esz, bytes, ncclChar, upper, comm, c->stream));
+            op(g_nccl.Recv(b + (size_t)(c->np - H) * c->plane * fl[f].esz, bytes, ncclChar, upper, comm, c->stream));
         }
     }
-    CET_NCCL(g_nccl.GroupEnd());
+    const ncclResult_t end = g_nccl.GroupEnd();
+    CET_NCCL(first);
+    CET_NCCL(end);
     if (fields & 1) c->nst_valid = false;      // ghost states changed (cet_sweep_run repairs the cache itself)
     if (fields & 2) {          // orientation unit vectors of the refreshed ghost planes
         if (lower >= 0) if (int rc = orient_update(c, 0, H)) return rc;
@@ -168,6 +170,7 @@ int cet_halo_exchange(cet_ctx *c, int fields)
 {
     CET_REQUIRE(c, "cet_halo_exchange: NULL ctx");
     cet::DeviceGuard dg(c->device);
+    lattice_changed(c);                  // the ghost planes of every derived array are stale
     return comm_halo_exchange(c, fields);
 }
 

@@ -115,8 +115,23 @@ struct cet_ctx {
     void *records = nullptr;
     size_t cap_records = 0;
     int64_t sweep_index = 0;
+    int64_t last_thermal_index = -1;  // sweep index whose thermal step has already run (priming pass)
     double *blk_sum = nullptr, *blk_max = nullptr, *plane_sum = nullptr;
     int64_t n_blk = 0;
+
+    // fused tile kernel (sweep_tile.cu): resident class codes + pair operands, TMA descriptors
+    uint8_t *cvox = nullptr;
+    double *pairop = nullptr;
+    int *tile_flag = nullptr;
+    bool tile_valid = false;          // cvox / pairop match vox / theta / phi / T / defects / the state ids
+    bool emp_canonical = false;       // no empty site carries an orientation (checked by tile_state_ensure)
+    bool stamps_pending = false;      // the last sweep's stamped sites still hold their old rate sums
+    bool tile_attr_set = false;
+    int debug_flags = 0;              // cet_debug_flags: 1 = no TMA (cooperative tile loads), 2 = gather kernels of the first design
+    alignas(64) unsigned char tmap_vox[128];
+    alignas(64) unsigned char tmap_po[128];
+    const void *tmap_vox_ptr = nullptr, *tmap_po_ptr = nullptr;
+    int n_sm = 0;                     // multiprocessors of the device (queried once)
 
     // grain clustering (grains.cu)
     int *grain_label = nullptr, *grain_gid = nullptr;
@@ -149,7 +164,10 @@ namespace cet {
 int ensure_stage(cet_ctx *c, size_t bytes);
 int orient_update(cet_ctx *c, int64_t p_lo, int64_t p_hi);
 int nst_build(cet_ctx *c, int p_lo, int p_hi);     // rebuild the neighbour-state cache of local planes [p_lo, p_hi)
-int nst_ensure(cet_ctx *c);                          // ... of every plane it can be built for, if it is stale   // v := unit_vector(theta, phi) on local planes
+int nst_ensure(cet_ctx *c);                          // ... of every plane it can be built for, if it is stale
+int sm_count(cet_ctx *c);                            // multiprocessors of the context's device
+// every writer of vox / theta / phi / T / defects other than the tile-aware sweep kernels calls this
+inline void lattice_changed(cet_ctx *c) { c->tile_valid = false; c->rates_valid = false; c->sweep_rates_valid = false; c->stamps_pending = false; }
 enum { PROF_DECIDE = 0, PROF_APPLY = 1, PROF_THERMAL = 2, PROF_RATES = 3, PROF_HALO = 4, PROF_STEP = 5, PROF_PICK = 6,
        PROF_REFRESH = 7, PROF_ALLREDUCE = 8, PROF_BOUNDARY = 9, PROF_KINDS = 10 };
 // RAII span: records an event pair around a launch when profiling is on.

@@ -204,7 +204,7 @@ extern "C" int cet_defects_refresh(cet_ctx *c, const double *draws, int64_t n_dr
     CET_CUDA(cudaMemcpyAsync(h, a.totals, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CET_CUDA(cudaStreamSynchronize(c->stream));
     if (n_defects) *n_defects = (int64_t)h[1];
-    c->rates_valid = false; c->sweep_rates_valid = false;            // defect factors changed (kmc_event_rates.py:94)
+    lattice_changed(c);                                              // defect factors changed (kmc_event_rates.py:94)
     if (apply_to_state && h[1]) c->nst_valid = false;
     return 0;
 }

@@ -12,6 +12,7 @@
 //
 // misorientation < t  <=>  arccos(clamp(v1.v2)) < t  <=>  clamp(v1.v2) > cos t, evaluated on the
 // resident unit vectors (kmc_event_rates.py:11-23).
+#include <algorithm>
 #include "ctx.cuh"
 #include "reduce.cuh"
 
@@ -148,7 +149,7 @@ int cet_grains_label(cet_ctx *c, double theta_threshold, int64_t *n_grains)
     unsigned int *cnt = (unsigned int *)c->stage;
     CET_CUDA(cudaMemsetAsync(cnt, 0, 64, c->stream));
     const int64_t lo = 0, hi = c->nloc;
-    const int grid = (int)((hi + 255) / 256 < 148 * 16 ? (hi + 255) / 256 : 148 * 16);
+    const int grid = (int)std::min<int64_t>((hi + 255) / 256, (int64_t)sm_count(c) * 16);
     grains_init_kernel<<<grid, 256, 0, c->stream>>>(c->vox, c->grain_label, lo, hi);
     grains_union_kernel<<<grid, 256, 0, c->stream>>>(c->vox, c->v, c->grain_label, (int)c->n1, 0, (int)c->np,
                                                      cos(theta_threshold));
@@ -177,7 +178,7 @@ int cet_grains_stats(cet_ctx *c, int64_t cap, int32_t *root, int32_t *size, int3
     GrainStat *st = nullptr;
     CET_CUDA(cudaMalloc(&st, (size_t)n * sizeof(GrainStat)));
     const int64_t lo = 0, hi = c->nloc;
-    const int grid = (int)((hi + 255) / 256 < 148 * 16 ? (hi + 255) / 256 : 148 * 16);
+    const int grid = (int)std::min<int64_t>((hi + 255) / 256, (int64_t)sm_count(c) * 16);
     grains_stats_init_kernel<<<grid, 256, 0, c->stream>>>(c->grain_label, c->grain_gid, lo, hi, st);
     grains_stats_kernel<<<grid, 256, 0, c->stream>>>(c->grain_label, c->grain_gid, lo, hi, st, (int)c->n1,
                                                      (int)(c->i_begin - c->halo));

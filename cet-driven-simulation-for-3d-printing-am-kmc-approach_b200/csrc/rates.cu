@@ -17,7 +17,6 @@
 #include "ctx.cuh"
 #include "rate_tile.cuh"
 #include <algorithm>
-#include <stdlib.h>
 #include "reduce.cuh"
 
 namespace cet {
@@ -35,17 +34,16 @@ __global__ void rate_tables_kernel(const cet_rate_params P, double *tab)
 }
 
 struct RateTileArgs;
+int sweep_flush(cet_ctx *c);      // sweep.cu
 template <int MINB>
 __global__ void rates_tile_kernel(const __grid_constant__ RateTileArgs a, int s_lo, int s_hi, unsigned int *queue);
 __global__ void dirty_eval_kernel(const __grid_constant__ RateTileArgs a, const int32_t *list, const unsigned int *n_list,
                                   unsigned int *queue);
 
-static int rate_tables_ensure(cet_ctx *c)
+int rate_tables_ensure(cet_ctx *c)
 {
     if (!c->rate_attr_set) {                 // per device; a context lives on one device
-        CET_CUDA(cudaFuncSetAttribute(rates_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
         CET_CUDA(cudaFuncSetAttribute(rates_tile_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
-        CET_CUDA(cudaFuncSetAttribute(rates_tile_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
         CET_CUDA(cudaFuncSetAttribute(dirty_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
         c->rate_attr_set = true;
     }
@@ -223,12 +221,9 @@ int rates_rows(cet_ctx *c, int p_lo, int p_hi)
         ProfScope ps(c, PROF_RATES);
         unsigned int *queue = (unsigned int *)(c->rate_tab + RT_TABLE_DOUBLES);
         CET_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned int), c->stream));
-        const int grid = (int)std::min<int64_t>(((int64_t)s_hi - s_lo + RT_CHUNK * RT_WARPS - 1) / (RT_CHUNK * RT_WARPS), 148 * 5);
-        static const int variant = getenv("CET_RT_MINB") ? atoi(getenv("CET_RT_MINB")) : 5;     // tuning knob (profiles/)
-        const int g6 = (int)std::min<int64_t>(((int64_t)s_hi - s_lo + RT_CHUNK * RT_WARPS - 1) / (RT_CHUNK * RT_WARPS), 148 * 6);
-        if (variant == 4) rates_tile_kernel<4><<<std::min(grid, 148 * 4), RT_THREADS, sizeof(RateSmem), c->stream>>>(a, s_lo, s_hi, queue);
-        else if (variant == 6) rates_tile_kernel<6><<<g6, RT_THREADS, sizeof(RateSmem), c->stream>>>(a, s_lo, s_hi, queue);
-        else rates_tile_kernel<5><<<grid, RT_THREADS, sizeof(RateSmem), c->stream>>>(a, s_lo, s_hi, queue);
+        const int grid = (int)std::min<int64_t>(((int64_t)s_hi - s_lo + RT_CHUNK * RT_WARPS - 1) / (RT_CHUNK * RT_WARPS),
+                                                (int64_t)sm_count(c) * 5);
+        rates_tile_kernel<5><<<grid, RT_THREADS, sizeof(RateSmem), c->stream>>>(a, s_lo, s_hi, queue);
     }
     CET_CUDA(cudaGetLastError());
     return 0;
@@ -248,7 +243,7 @@ int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint32_t *stamp, int3
     dirty_scan_kernel<<<(n_words + RB_WARPS * 32 - 1) / (RB_WARPS * 32), RB_WARPS * 32, 0, c->stream>>>(d);
     CET_CUDA(cudaGetLastError());
     const int64_t nsite = (int64_t)(p_hi - p_lo) * c->plane;
-    const int grid = (int)std::min<int64_t>((nsite + RT_CHUNK * RT_WARPS - 1) / (RT_CHUNK * RT_WARPS), 148 * 5);
+    const int grid = (int)std::min<int64_t>((nsite + RT_CHUNK * RT_WARPS - 1) / (RT_CHUNK * RT_WARPS), (int64_t)sm_count(c) * 5);
     unsigned int *queue = (unsigned int *)(c->rate_tab + RT_TABLE_DOUBLES) + 1;
     CET_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned int), c->stream));
     dirty_eval_kernel<<<grid, RT_THREADS, sizeof(RateSmem), c->stream>>>(tile_args(c), list, counter, queue);
@@ -416,6 +411,7 @@ int cet_rates_download(cet_ctx *c, double *site_rate, double *dep_rate)
     CET_REQUIRE(c, "cet_rates_download: NULL ctx");
     CET_REQUIRE(c->rates_valid || c->sweep_rates_valid, "cet_rates_download: rates are stale (call cet_rates_build)");
     cet::DeviceGuard dg(c->device);
+    if (int rc = sweep_flush(c)) return rc;          // the fused sweep path refreshes lazily
     if (site_rate)
         CET_CUDA(cudaMemcpyAsync(site_rate, c->site_rate + c->owned_offset(), (size_t)c->owned_sites() * 8,
                                  cudaMemcpyDeviceToHost, c->stream));

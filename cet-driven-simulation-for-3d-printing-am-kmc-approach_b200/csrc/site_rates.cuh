@@ -330,13 +330,19 @@ CET_HD EmpPrep emp_prep(const cet_rate_params &P, double T_self, double T_km, do
 
 // rate of the attachment event copying an occupied neighbour of species energy hE = 0.5 * E_b[ia]
 // (ia = 0 W, 1 Re, 2 C); returns 0 when filtered (:157)
+// E_att = 0.5 * E_b * (1 - cos(mis)) from the clamped dot product of the two unit vectors (:23,:155)
+CET_HD double att_E(double hE, double dot) { return hE * (1.0 - pymax(pymin(dot, 1.0), -1.0)); }
+CET_HD double att_pair_rate_E(const cet_rate_params &P, double E_att, double inv_kTT, double ng,
+                              const double *exp_tab = CET_EXP2_TAB)
+{
+    return keep_rate(P, fast_exp_t(-E_att * inv_kTT, exp_tab) * ng);
+}
 CET_HD double att_pair_rate(const cet_rate_params &P, double hE, double inv_kTT, double ng, double sx, double sy,
                             double sz, double nx, double ny, double nz, const double *exp_tab = CET_EXP2_TAB)
 {
-    double dot = fma(sz, nz, fma(sy, ny, sx * nx));
-    dot = pymax(pymin(dot, 1.0), -1.0);
-    const double E_att = hE * (1.0 - dot);
-    return keep_rate(P, fast_exp_t(-E_att * inv_kTT, exp_tab) * ng);
+    // an empty site that carries no orientation has s = (0, 0, 1) and the dot product is nz bit for bit:
+    // the tile kernel (sweep_tile.cu) keeps att_E(hE, nz) resident per occupied site for that case
+    return att_pair_rate_E(P, att_E(hE, fma(sz, nz, fma(sy, ny, sx * nx))), inv_kTT, ng, exp_tab);
 }
 
 CET_HD int species_index(const cet_rate_params &P, int st)

@@ -29,9 +29,12 @@
 // sweep (comm.cu) the rates of the evaluated ghost planes and of the two outermost owned planes
 // are rebuilt densely (6 planes per cut face).  Plane sums are combined in a fixed order so the trajectory is independent of the
 // number of slabs.
+#include <algorithm>
 #include "ctx.cuh"
 #include "rate_tile.cuh"
 #include "reduce.cuh"
+#include "philox.cuh"
+#include "tile_state.cuh"
 
 namespace cet {
 
@@ -40,31 +43,14 @@ int rates_rows(cet_ctx *c, int p_lo, int p_hi);                                 
 int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint32_t *stamp, int32_t *list, unsigned int *counter);
 int comm_sweep_reduce(cet_ctx *c, double *plane_sum, int n, double *max_inout);   // comm.cu
 int comm_halo_exchange(cet_ctx *c, int fields);
-
-// ---- Philox4x32-10 ------------------------------------------------------------------------
-struct u32x4 { uint32_t x, y, z, w; };
-__device__ __forceinline__ u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1)
-{
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = u32x4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    return c;
-}
-// two uniforms in [0,1) with 53 random bits each, keyed by the global site
-__device__ __forceinline__ void philox_u2(uint64_t seed, uint64_t site, uint32_t sweep, uint32_t stream,
-                                          double *u0, double *u1)
-{
-    const u32x4 r = philox4x32_10(u32x4{(uint32_t)site, (uint32_t)(site >> 32), sweep, stream},
-                                  (uint32_t)seed, (uint32_t)(seed >> 32));
-    const uint64_t a = ((uint64_t)r.x << 32) | r.y, b = ((uint64_t)r.z << 32) | r.w;
-    *u0 = (double)(a >> 11) * 1.1102230246251565e-16;
-    *u1 = (double)(b >> 11) * 1.1102230246251565e-16;
-}
-enum { STREAM_FIRE = 0, STREAM_PICK = 1, STREAM_ANGLES = 2, STREAM_SPECIES = 3, STREAM_DEFECT = 4, STREAM_FIRE_REST = 5 };
+// sweep_tile.cu — the fused tile kernel (refresh + stream) and the arrays it stages
+enum { TM_ALL = 1, TM_STREAM = 2 };
+int tile_state_ensure(cet_ctx *c);
+int tile_state_build(cet_ctx *c, int p_lo, int p_hi);
+int tile_pairop_T_update(cet_ctx *c);
+int tile_pass(cet_ctx *c, int p_lo, int p_hi, int mode, uint64_t seed, uint32_t sweep);
+int tile_parts_per_plane(const cet_ctx *c);
+int stamp_fill(cet_ctx *c, int p_lo, int p_hi);
 
 struct Record {          // one fired event
     int32_t src;         // local linear index of the source site
@@ -355,7 +341,21 @@ struct ApplyArgs {
     uint64_t seed;
     uint32_t sweep;
     double defect_fraction;
+    // tile state of sweep_tile.cu, kept in step with the lattice (NULL: the gather kernels run instead)
+    uint8_t *cvox;
+    double *pairop;
+    const double *T;
+    uint64_t tlut;
 };
+
+// cvox / pairop of a site that now holds `state` with orientation z component z
+__device__ __forceinline__ void tile_put(const ApplyArgs &a, int site, int state, double z)
+{
+    if (!a.cvox) return;
+    const unsigned code = (unsigned)(a.tlut >> (4 * state)) & 15u;
+    a.cvox[site] = (uint8_t)((a.vox[site] & 0xF0) | code);
+    a.pairop[site] = code == TC_EMPTY ? a.T[site] : tile_pairop(a.P, code, 0.0, z);
+}
 
 // A site changed state: request a refresh of the site and of its neighbours.  The refresh pass
 // (rates.cu) re-evaluates every site whose stamp bit is set and rewrites its cached neighbour-class
@@ -415,11 +415,14 @@ __global__ void __launch_bounds__(128) sweep_apply_kernel(const __grid_constant_
                 a.vox[s] = (uint8_t)(a.vox[s] & 0xF0);
                 a.theta[s] = 0.0; a.phi[s] = 0.0;
                 a.v[s] = Vec4{0.0, 0.0, 1.0, 0.0};
+                tile_put(a, tgt, src_state, uv.z);
+                tile_put(a, s, 0, 1.0);
                 upd = tgt;
             } else {                                                     // dep / nuc / att
                 a.vox[s] = (uint8_t)((a.vox[s] & 0xF0) | eatom);
                 a.theta[s] = rec.theta; a.phi[s] = rec.phi;
                 a.v[s] = uv;
+                tile_put(a, s, eatom, uv.z);
                 if (ety == CET_EV_NUC && owned) ++nuc;
             }
             int upd_state = ety == CET_EV_DIFF ? src_state : eatom;      // what the filled site holds
@@ -430,6 +433,7 @@ __global__ void __launch_bounds__(128) sweep_apply_kernel(const __grid_constant_
                     a.vox[upd] = (uint8_t)((a.vox[upd] & 0xF0) | a.P.defect_id);
                     a.theta[upd] = 0.0; a.phi[upd] = 0.0;
                     a.v[upd] = Vec4{0.0, 0.0, 1.0, 0.0};
+                    tile_put(a, upd, a.P.defect_id, 1.0);
                     upd_state = a.P.defect_id;
                 }
             }
@@ -483,7 +487,7 @@ static int sweep_alloc(cet_ctx *c)
         CET_CUDA(cudaMalloc(&c->records, c->cap_fired * sizeof(Record)));
         c->cap_records = c->cap_fired;
     }
-    const int tpp = (int)((c->plane + ST_TILE - 1) / ST_TILE);
+    const int tpp = std::max((int)((c->plane + ST_TILE - 1) / ST_TILE), tile_parts_per_plane(c));
     if (!c->blk_sum) {
         c->n_blk = (int64_t)tpp * c->np;
         CET_CUDA(cudaMalloc(&c->blk_sum, (size_t)c->n_blk * sizeof(double)));
@@ -518,6 +522,7 @@ extern "C" int cet_sweep_reset(cet_ctx *c)
     cet::DeviceGuard dg(c->device);
     if (c->sweep) CET_CUDA(cudaMemsetAsync(c->sweep, 0, sizeof(SweepState), c->stream));
     c->sweep_index = 0;
+    c->last_thermal_index = -1;
     c->T_finite = false;          // a terminated run skips its stencil passes: re-check T next time
     return 0;
 }
@@ -554,9 +559,153 @@ extern "C" int cet_sweep_set_state(cet_ctx *c, int64_t sweep_index, double tau, 
     CET_CUDA(cudaMemcpyAsync(c->sweep, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
     CET_CUDA(cudaStreamSynchronize(c->stream));
     c->sweep_index = sweep_index;
-    c->sweep_rates_valid = false;
+    c->last_thermal_index = -1;
+    c->sweep_rates_valid = false; c->stamps_pending = false;
     return 0;
 }
+
+namespace cet {
+
+// One sweep.  The fused path (sweep_tile.cu) needs the orientation invariant of tile_state.cuh; the
+// gather path is the first design (stream, pick, apply, stamp scan + list-driven re-evaluation).
+// count == false is the priming pass of a fresh clock: tau is still 0, nothing can fire, and the pass
+// only measures the totals that give the first real sweep its interval.
+static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_params *tp, const SlabRanges &R, bool fused,
+                      bool count)
+{
+    const int n_eval = R.eval_hi - R.eval_lo;
+    const int i_off = (int)(c->i_begin - c->halo);
+    const int top_plane = (int)(c->n0 - 1 - i_off);
+    double *max_slot = c->plane_sum + c->n0;      // plane_sum[n0] holds the running max
+    ProfScope step_scope(c, PROF_STEP);
+    if (sp->thermal_every > 0 && c->sweep_index % sp->thermal_every == 0 && c->last_thermal_index != c->sweep_index) {
+        if (int rc = thermal_cet_step(c, tp, &c->sweep->terminated)) return rc;      // clears sweep_rates_valid
+        if (c->world > 1) if (int rc = comm_halo_exchange(c, 4)) return rc;
+        if (fused) if (int rc = tile_pairop_T_update(c)) return rc;
+        c->last_thermal_index = c->sweep_index;
+    }
+    sweep_reset_kernel<<<1, 1, 0, c->stream>>>(c->sweep, max_slot);
+    CET_CUDA(cudaMemsetAsync(c->plane_sum, 0, (size_t)c->n0 * sizeof(double), c->stream));
+    int parts;
+    if (fused) {
+        // refresh (the stamped sites of the previous sweep, or every site after a thermal step / upload)
+        // and the fire test of this sweep in one pass
+        const bool all = !c->sweep_rates_valid;
+        {
+            ProfScope ps(c, all ? PROF_RATES : PROF_DECIDE);
+            if (int rc = tile_pass(c, R.eval_lo, R.eval_hi, (all ? TM_ALL : 0) | TM_STREAM, sp->seed, (uint32_t)c->sweep_index))
+                return rc;
+        }
+        c->sweep_rates_valid = true;
+        CET_CUDA(cudaMemsetAsync(c->stamp, 0, (size_t)c->nloc / 8 + 8, c->stream));      // consumed; apply sets the next ones
+        parts = tile_parts_per_plane(c);
+    } else {
+        if (!c->sweep_rates_valid) {                 // new lattice, new T or new parameters: dense rebuild
+            if (int rc = rates_rows(c, R.eval_lo, R.eval_hi)) return rc;
+            c->sweep_rates_valid = true;
+        }
+        CET_CUDA(cudaMemsetAsync(c->stamp, 0, (size_t)c->nloc / 8 + 8, c->stream));      // stamp bitmap of this sweep
+        const int tpp = (int)((c->plane + ST_TILE - 1) / ST_TILE);
+        StreamArgs a;
+        a.site_rate = c->site_rate; a.dep_rate = c->dep_rate; a.ss = c->sweep;
+        a.fired = c->fired; a.cap_fired = (unsigned int)c->cap_fired;
+        a.blk_sum = c->blk_sum; a.blk_max = c->blk_max;
+        a.p_lo = R.eval_lo;
+        a.top_plane = (top_plane >= R.eval_lo && top_plane < R.eval_hi) ? top_plane : -1;
+        a.plane_sites = (int)c->plane; a.tiles_per_plane = tpp; a.i_off = i_off;
+        a.seed = sp->seed; a.sweep = (uint32_t)c->sweep_index;
+        ProfScope ps(c, PROF_DECIDE);
+        sweep_stream_kernel<<<n_eval * tpp, ST_THREADS, 0, c->stream>>>(a);
+        parts = tpp;
+    }
+    CET_CUDA(cudaGetLastError());
+    sweep_plane_reduce_kernel<<<(n_eval + 3) / 4, 128, 0, c->stream>>>(
+        c->blk_sum, c->blk_max, parts, n_eval, i_off + R.eval_lo, (int)c->i_begin, (int)c->i_end,
+        c->plane_sum, max_slot);
+    CET_CUDA(cudaGetLastError());
+    const int sparse_grid = sm_count(c) * 32;
+    {
+        PickArgs a;
+        a.g = c->lat(); a.theta = c->theta; a.phi = c->phi; a.site_rate = c->site_rate; a.dep_rate = c->dep_rate;
+        a.P = c->rp; a.ss = c->sweep; a.fired = c->fired; a.cap_fired = (unsigned int)c->cap_fired;
+        a.records = (Record *)c->records; a.claim = c->claim;
+        a.seed = sp->seed; a.sweep = (uint32_t)c->sweep_index;
+        ProfScope ps(c, PROF_PICK);
+        sweep_pick_kernel<<<sparse_grid, 128, 0, c->stream>>>(a);
+    }
+    CET_CUDA(cudaGetLastError());
+    {
+        ApplyArgs b;
+        b.vox = c->vox; b.theta = c->theta; b.phi = c->phi; b.v = c->v;
+        b.ss = c->sweep; b.records = (const Record *)c->records; b.cap_fired = (unsigned int)c->cap_fired;
+        b.claim = c->claim; b.stamp = c->stamp; b.nst = (unsigned long long *)c->nst;
+        b.P = c->rp; b.L = (int)c->n1; b.n0 = (int)c->n0; b.i_off = i_off; b.np = (int)c->np;
+        b.c_lo = R.claim_lo; b.c_hi = R.claim_hi; b.own_lo = R.own_lo; b.own_hi = R.own_hi;
+        b.seed = sp->seed; b.sweep = (uint32_t)c->sweep_index;
+        b.defect_fraction = sp->defect_fraction;
+        b.cvox = fused ? c->cvox : nullptr; b.pairop = c->pairop; b.T = c->T; b.tlut = tile_code_lut(c->rp);
+        ProfScope ps(c, PROF_APPLY);
+        sweep_apply_kernel<<<sparse_grid, 128, 0, c->stream>>>(b);
+    }
+    CET_CUDA(cudaGetLastError());
+    if (!fused) {
+        ProfScope ps(c, PROF_REFRESH);
+        if (int rc = rates_rows_dirty(c, R.eval_lo, R.eval_hi, c->stamp, c->dirty, &c->sweep->n_dirty)) return rc;
+    }
+    // the totals are only needed for the next tau: reduce them here, next to the halo exchange, so
+    // that a sweep has one inter-rank synchronisation point instead of two
+    if (c->world > 1) {
+        ProfScope ps(c, PROF_ALLREDUCE);
+        if (int rc = comm_sweep_reduce(c, c->plane_sum, (int)c->n0, max_slot)) return rc;
+    }
+    sweep_finalize_kernel<<<1, 256, 0, c->stream>>>(c->sweep, c->plane_sum, (int)c->n0, max_slot,
+                                                    sp->events_per_sweep, sp->p_max);
+    CET_CUDA(cudaGetLastError());
+    if (c->world > 1 && count) {
+        {
+            ProfScope ps(c, PROF_HALO);
+            if (int rc = comm_halo_exchange(c, 1 | 2)) return rc;
+        }
+        ProfScope pb(c, PROF_BOUNDARY);
+        // The ghost planes now hold the owners' lattice.  Events this slab could not resolve
+        // (write set reaching beyond ghost depth 2) may have changed ghost planes that the two
+        // outermost owned planes read, so the evaluated ghost planes and those two owned planes on
+        // each cut face are re-evaluated: densely here (gather path), or by stamping them for the
+        // refresh of the next fused pass.
+        if (fused) {
+            if (int rc = tile_state_build(c, 0, R.own_lo)) return rc;
+            if (int rc = tile_state_build(c, R.own_hi, (int)c->np)) return rc;
+            if (R.own_lo > R.eval_lo) if (int rc = stamp_fill(c, R.eval_lo, R.own_lo + 2)) return rc;
+            if (R.eval_hi > R.own_hi) if (int rc = stamp_fill(c, R.own_hi - 2, R.eval_hi)) return rc;
+        } else {
+            c->nst_valid = true;       // the exchange marked the whole cache stale; only the planes rebuilt below are
+            if (R.own_lo > R.eval_lo) {
+                if (int rc = nst_build(c, R.eval_lo, R.own_lo + 2)) return rc;
+                if (int rc = rates_rows(c, R.eval_lo, R.own_lo + 2)) return rc;
+            }
+            if (R.eval_hi > R.own_hi) {
+                if (int rc = nst_build(c, R.own_hi - 2, R.eval_hi)) return rc;
+                if (int rc = rates_rows(c, R.own_hi - 2, R.eval_hi)) return rc;
+            }
+        }
+    }
+    if (count) c->sweep_index++;
+    return 0;
+}
+
+// Bring the resident rate sums up to date with the lattice (the fused path refreshes the sites an
+// event touched at the START of the next sweep): one refresh-only pass over the stamped sites.
+int sweep_flush(cet_ctx *c)
+{
+    if (!c->stamps_pending || !c->sweep_rates_valid || !c->tile_valid) return 0;
+    const SlabRanges R = slab_ranges(c);
+    if (int rc = tile_pass(c, R.eval_lo, R.eval_hi, 0, 0, 0)) return rc;
+    CET_CUDA(cudaMemsetAsync(c->stamp, 0, (size_t)c->nloc / 8 + 8, c->stream));
+    c->stamps_pending = false;
+    return 0;
+}
+
+}  // namespace cet
 
 extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_params *sp,
                              const cet_thermal_params *tp, cet_sweep_result *res)
@@ -573,106 +722,37 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
     cet::DeviceGuard dg(c->device);
     if (int rc = sweep_alloc(c)) return rc;
     const SlabRanges R = slab_ranges(c);
-    const int tpp = (int)((c->plane + ST_TILE - 1) / ST_TILE);
-    const int n_eval = R.eval_hi - R.eval_lo;
-    const int i_off = (int)(c->i_begin - c->halo);
-    const int top_plane = (int)(c->n0 - 1 - i_off);
-    double *max_slot = c->plane_sum + c->n0;      // plane_sum[n0] holds the running max
 
     SweepState before;
     CET_CUDA(cudaMemcpyAsync(&before, c->sweep, sizeof(before), cudaMemcpyDeviceToHost, c->stream));
     CET_CUDA(cudaStreamSynchronize(c->stream));
 
-    if (int rc = nst_ensure(c)) return rc;        // the apply kernel maintains the cache from here on
-    for (int64_t n = 0; n < n_sweeps; ++n) {
-        ProfScope step_scope(c, PROF_STEP);
-        if (sp->thermal_every > 0 && c->sweep_index % sp->thermal_every == 0) {
-            if (int rc = thermal_cet_step(c, tp, &c->sweep->terminated)) return rc;
-            if (c->world > 1) if (int rc = comm_halo_exchange(c, 4)) return rc;
-        }
-        if (!c->sweep_rates_valid) {                 // new lattice, new T or new parameters: dense rebuild
-            if (int rc = rates_rows(c, R.eval_lo, R.eval_hi)) return rc;
-            c->sweep_rates_valid = true;
-        }
-        CET_CUDA(cudaMemsetAsync(c->stamp, 0, (size_t)c->nloc / 8 + 8, c->stream));      // stamp bitmap of this sweep
-        sweep_reset_kernel<<<1, 1, 0, c->stream>>>(c->sweep, max_slot);
-        CET_CUDA(cudaMemsetAsync(c->plane_sum, 0, (size_t)c->n0 * sizeof(double), c->stream));
-        {
-            StreamArgs a;
-            a.site_rate = c->site_rate; a.dep_rate = c->dep_rate; a.ss = c->sweep;
-            a.fired = c->fired; a.cap_fired = (unsigned int)c->cap_fired;
-            a.blk_sum = c->blk_sum; a.blk_max = c->blk_max;
-            a.p_lo = R.eval_lo;
-            a.top_plane = (top_plane >= R.eval_lo && top_plane < R.eval_hi) ? top_plane : -1;
-            a.plane_sites = (int)c->plane; a.tiles_per_plane = tpp; a.i_off = i_off;
-            a.seed = sp->seed; a.sweep = (uint32_t)c->sweep_index;
-            ProfScope ps(c, PROF_DECIDE);
-            sweep_stream_kernel<<<n_eval * tpp, ST_THREADS, 0, c->stream>>>(a);
-        }
-        CET_CUDA(cudaGetLastError());
-        sweep_plane_reduce_kernel<<<(n_eval + 3) / 4, 128, 0, c->stream>>>(
-            c->blk_sum, c->blk_max, tpp, n_eval, i_off + R.eval_lo, (int)c->i_begin, (int)c->i_end,
-            c->plane_sum, max_slot);
-        CET_CUDA(cudaGetLastError());
-        {
-            PickArgs a;
-            a.g = c->lat(); a.theta = c->theta; a.phi = c->phi; a.site_rate = c->site_rate; a.dep_rate = c->dep_rate;
-            a.P = c->rp; a.ss = c->sweep; a.fired = c->fired; a.cap_fired = (unsigned int)c->cap_fired;
-            a.records = (Record *)c->records; a.claim = c->claim;
-            a.seed = sp->seed; a.sweep = (uint32_t)c->sweep_index;
-            ProfScope ps(c, PROF_PICK);
-            sweep_pick_kernel<<<148 * 32, 128, 0, c->stream>>>(a);
-        }
-        CET_CUDA(cudaGetLastError());
-        {
-            ApplyArgs b;
-            b.vox = c->vox; b.theta = c->theta; b.phi = c->phi; b.v = c->v;
-            b.ss = c->sweep; b.records = (const Record *)c->records; b.cap_fired = (unsigned int)c->cap_fired;
-            b.claim = c->claim; b.stamp = c->stamp; b.nst = (unsigned long long *)c->nst;
-            b.P = c->rp; b.L = (int)c->n1; b.n0 = (int)c->n0; b.i_off = i_off; b.np = (int)c->np;
-            b.c_lo = R.claim_lo; b.c_hi = R.claim_hi; b.own_lo = R.own_lo; b.own_hi = R.own_hi;
-            b.seed = sp->seed; b.sweep = (uint32_t)c->sweep_index;
-            b.defect_fraction = sp->defect_fraction;
-            ProfScope ps(c, PROF_APPLY);
-            sweep_apply_kernel<<<148 * 32, 128, 0, c->stream>>>(b);
-        }
-        CET_CUDA(cudaGetLastError());
-        {
-            ProfScope ps(c, PROF_REFRESH);
-            if (int rc = rates_rows_dirty(c, R.eval_lo, R.eval_hi, c->stamp, c->dirty, &c->sweep->n_dirty))
-                return rc;
-        }
-        // the totals are only needed for the next tau: reduce them here, next to the halo exchange, so
-        // that a sweep has one inter-rank synchronisation point instead of two
-        if (c->world > 1) {
-            ProfScope ps(c, PROF_ALLREDUCE);
-            if (int rc = comm_sweep_reduce(c, c->plane_sum, (int)c->n0, max_slot)) return rc;
-        }
-        sweep_finalize_kernel<<<1, 256, 0, c->stream>>>(c->sweep, c->plane_sum, (int)c->n0, max_slot,
-                                                        sp->events_per_sweep, sp->p_max);
-        CET_CUDA(cudaGetLastError());
-        if (c->world > 1) {
-            {
-                ProfScope ps(c, PROF_HALO);
-                if (int rc = comm_halo_exchange(c, 1 | 2)) return rc;
-            }
-            ProfScope pb(c, PROF_BOUNDARY);
-            c->nst_valid = true;       // the exchange marked the whole cache stale; only the planes rebuilt below are
-            // The ghost planes now hold the owners' lattice.  Events this slab could not resolve
-            // (write set reaching beyond ghost depth 2) may have changed ghost planes that the two
-            // outermost owned planes read, so the dense rebuild covers the evaluated ghost planes
-            // and those two owned planes on each cut face.
-            if (R.own_lo > R.eval_lo) {
-                if (int rc = nst_build(c, R.eval_lo, R.own_lo + 2)) return rc;
-                if (int rc = rates_rows(c, R.eval_lo, R.own_lo + 2)) return rc;
-            }
-            if (R.eval_hi > R.own_hi) {
-                if (int rc = nst_build(c, R.own_hi - 2, R.eval_hi)) return rc;
-                if (int rc = rates_rows(c, R.own_hi - 2, R.eval_hi)) return rc;
-            }
-        }
-        c->sweep_index++;
+    // Which kernels: the fused tile pass when no empty site carries an orientation (the reference's
+    // invariant, checked here on the device), the gather kernels otherwise.  A change of path drops
+    // the state only the other path maintains.
+    bool fused = !(c->debug_flags & 2);
+    if (fused) {
+        if (!c->tile_valid) { c->sweep_rates_valid = false; c->stamps_pending = false; }
+        if (int rc = tile_state_ensure(c)) return rc;
+        fused = c->emp_canonical;
     }
+    if (c->world > 1) {                      // every slab must take the same path
+        double f = fused ? 0.0 : 1.0;
+        if (int rc = cet_allreduce_f64(c, &f, 1, 1)) return rc;
+        fused = f == 0.0;
+    }
+    if (fused) {
+        c->nst_valid = false;                // the fused path keeps no neighbour cache
+    } else {
+        if (c->stamps_pending) { c->sweep_rates_valid = false; c->stamps_pending = false; }
+        c->tile_valid = false;               // the gather path's apply does not maintain cvox / pairop
+        if (int rc = nst_ensure(c)) return rc;
+    }
+    if (n_sweeps > 0 && before.tau == 0.0 && !before.terminated)
+        if (int rc = sweep_once(c, sp, tp, R, fused, false)) return rc;
+    for (int64_t n = 0; n < n_sweeps; ++n)
+        if (int rc = sweep_once(c, sp, tp, R, fused, true)) return rc;
+    if (fused && n_sweeps > 0) c->stamps_pending = true;
     c->rates_valid = false;          // the BKL sum hierarchy is not maintained by the sweeps
     SweepState after;
     CET_CUDA(cudaMemcpyAsync(&after, c->sweep, sizeof(after), cudaMemcpyDeviceToHost, c->stream));

@@ -301,6 +301,7 @@ int cet_thermal_cet(cet_ctx *c, const cet_thermal_params *p)
 {
     CET_REQUIRE(c && p, "cet_thermal_cet: NULL argument");
     cet::DeviceGuard dg(c->device);
+    c->tile_valid = false; c->stamps_pending = false;
     return thermal_cet_step(c, p, nullptr);
 }
 
@@ -319,6 +320,7 @@ int cet_thermal_full(cet_ctx *c, const cet_thermal_full_params *p, const double 
     a.dt = p->dt; a.alpha = p->alpha; a.rho_cp = p->rho_cp; a.latent_over_cp = p->latent_over_cp;
     a.inv_dt_latent = 1.0 / (p->dt > 1e-12 ? p->dt : 1e-12);   // mask / max(dt, 1e-12), thermal_solver.py:98
     int rc = launch_thermal<true>(c, a);
+    c->tile_valid = false; c->stamps_pending = false;
     if (rc) return rc;
     CET_CUDA(cudaStreamSynchronize(c->stream));   // q_top host pointer is borrowed for the call only
     return 0;
@@ -328,10 +330,10 @@ int cet_thermal_fill_gradient(cet_ctx *c, double t0, double g)
 {
     CET_REQUIRE(c, "cet_thermal_fill_gradient: NULL ctx");
     cet::DeviceGuard dg(c->device);
-    fill_gradient_kernel<<<148 * 8, 256, 0, c->stream>>>(c->T, c->plane, (int)c->np,
+    fill_gradient_kernel<<<sm_count(c) * 8, 256, 0, c->stream>>>(c->T, c->plane, (int)c->np,
                                                          (int)(c->i_begin - c->halo), (int)c->n0, t0, g);
     CET_CUDA(cudaGetLastError());
-    c->rates_valid = false; c->sweep_rates_valid = false;
+    lattice_changed(c);
     return 0;
 }
 

@@ -8,7 +8,7 @@ code on seeded inputs:
     traj_*.npz        run_kmc (kmc_simulation.py:203) final arrays + metrics.csv rows
     grains_*.npz      utils.get_clusters / metrics.compute_metrics (utils.py:69, metrics.py:41)
     defects_*.npz     defects.introduce_defects (defects.py:25)
-Usage:  python oracle/gen_golden.py [--grains-only | --defects-only]
+Usage:  python oracle/gen_golden.py [--grains-only | --defects-only | --traj NAME]
 """
 import io
 import os
@@ -92,6 +92,44 @@ def defects_cases(ref):
         print(f"defects_{name}: L={L} carbon={(st == 3).sum()} masked={mask.sum()} / {mask_noT.sum()} (no T)")
 
 
+# run_kmc trajectories.  The L30 cases are the main.py default (main.py:33-64: L=30,
+# defect_fraction=DEFECT_PROB=3e-3, n_seeds=20, one run per carbon level), shortened from 20 000 to
+# 2 001 steps (~3 min of reference time each); generate them with --traj NAME (they run in parallel).
+TRAJ_CASES = {
+    "L10_c01_def": dict(L=10, n_steps=401, temp=2800, defect_fraction=3e-3, n_seeds=5, impurity_c=0.1),
+    "L8_c00": dict(L=8, n_steps=250, temp=2800, defect_fraction=0.0, n_seeds=4, impurity_c=0.0),
+    "L12_c02_def": dict(L=12, n_steps=601, temp=2800, defect_fraction=0.02, n_seeds=8, impurity_c=0.2),
+    "L30_c00": dict(L=30, n_steps=2001, temp=2800, defect_fraction=3e-3, n_seeds=20, impurity_c=0.0),
+    "L30_c01": dict(L=30, n_steps=2001, temp=2800, defect_fraction=3e-3, n_seeds=20, impurity_c=0.1),
+    "L30_c02": dict(L=30, n_steps=2001, temp=2800, defect_fraction=3e-3, n_seeds=20, impurity_c=0.2),
+}
+
+
+def traj_case(ref, name):
+    import pandas as pd
+    km = ref["kmc_simulation"]
+    kw = TRAJ_CASES[name]
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            ref["nb_seed"](42)
+            stdout, sys.stdout = sys.stdout, io.StringIO()
+            try:
+                state, atom_type, total_time, theta, phi = km.run_kmc(output_prefix="g", **kw)
+            finally:
+                sys.stdout = stdout
+            df = pd.read_csv(os.path.join("outputs", "g", "metrics.csv"))
+        finally:
+            os.chdir(cwd)
+    cols = {f"csv_{c}": df[c].to_numpy() for c in df.columns if c not in ("CET_Class",)}
+    cols["csv_CET_Class"] = np.array(df["CET_Class"].tolist())
+    np.savez_compressed(os.path.join(OUT, f"traj_{name}.npz"), state=state.astype(np.int8),
+                        atom_type=atom_type.astype(np.int8), theta=theta, phi=phi,
+                        total_time=np.float64(total_time), kwargs=np.array(repr(kw)), **cols)
+    print(f"traj_{name}: occupied={int((state != 0).sum())} rows={len(df)} time={total_time:.3e}")
+
+
 def main():
     ref = refharness.load()
     os.makedirs(OUT, exist_ok=True)
@@ -100,6 +138,9 @@ def main():
         return
     if "--defects-only" in sys.argv:
         defects_cases(ref)
+        return
+    if "--traj" in sys.argv:
+        traj_case(ref, sys.argv[sys.argv.index("--traj") + 1])
         return
     li, ts, km = ref["lattice_init"], ref["thermal_solver"], ref["kmc_simulation"]
 
@@ -146,30 +187,9 @@ def main():
     grains_cases(ref)
     defects_cases(ref)
 
-    # ---- trajectories ------------------------------------------------------------------------
-    import pandas as pd
-    for name, kw in (("L10_c01_def", dict(L=10, n_steps=401, temp=2800, defect_fraction=3e-3, n_seeds=5, impurity_c=0.1)),
-                     ("L8_c00", dict(L=8, n_steps=250, temp=2800, defect_fraction=0.0, n_seeds=4, impurity_c=0.0)),
-                     ("L12_c02_def", dict(L=12, n_steps=601, temp=2800, defect_fraction=0.02, n_seeds=8, impurity_c=0.2))):
-        cwd = os.getcwd()
-        with tempfile.TemporaryDirectory() as tmp:
-            os.chdir(tmp)
-            try:
-                ref["nb_seed"](42)
-                stdout, sys.stdout = sys.stdout, io.StringIO()
-                try:
-                    state, atom_type, total_time, theta, phi = km.run_kmc(output_prefix="g", **kw)
-                finally:
-                    sys.stdout = stdout
-                df = pd.read_csv(os.path.join("outputs", "g", "metrics.csv"))
-            finally:
-                os.chdir(cwd)
-        cols = {f"csv_{c}": df[c].to_numpy() for c in df.columns if c not in ("CET_Class",)}
-        cols["csv_CET_Class"] = np.array(df["CET_Class"].tolist())
-        np.savez_compressed(os.path.join(OUT, f"traj_{name}.npz"), state=state.astype(np.int8),
-                            atom_type=atom_type.astype(np.int8), theta=theta, phi=phi,
-                            total_time=np.float64(total_time), kwargs=np.array(repr(kw)), **cols)
-        print(f"traj_{name}: occupied={int((state != 0).sum())} rows={len(df)} time={total_time:.3e}")
+    for name in TRAJ_CASES:
+        if not name.startswith("L30"):
+            traj_case(ref, name)
 
 
 if __name__ == "__main__":

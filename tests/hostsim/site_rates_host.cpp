@@ -55,3 +55,62 @@ extern "C" void hostsim_nst_words(const uint8_t *vox, int L, const cet_rate_para
                 out[s] = nst_word(lut, vox, s, i, j, k, L, L);
             }
 }
+
+// The fused sweep kernel's per-site evaluation (tile_state.cuh: class codes, pairop, tile_site_prep,
+// tile_pair_rate) run site by site on the host: `tile` receives its rate sums, `general` those of
+// site_rate_sum (the per-event code).  On lattices whose empty sites carry no orientation the two
+// must agree bit for bit.  Returns the number of empty sites that carry an orientation.
+#include "../../cet-driven-simulation-for-3d-printing-am-kmc-approach_b200/csrc/tile_state.cuh"
+extern "C" long long hostsim_tile_rates(const uint8_t *vox, const double *theta, const double *phi, const double *T,
+                                        int L, const cet_rate_params *P, double *tile, double *general)
+{
+    const long long LL = (long long)L * L, N = LL * L;
+    std::vector<Vec4> v(N);
+    for (long long q = 0; q < N; ++q) v[q] = unit_vec4(theta[q], phi[q]);
+    Lat g;
+    g.vox = vox; g.v = v.data(); g.T = T; g.L = L; g.n0 = L; g.i_off = 0;
+    std::vector<double> tab(RT_TABLE_DOUBLES);
+    for (int t = 0; t < 256; ++t) tab[RT_KEFF + t] = nuc_K_eff(*P, t >> 4, t & 15);
+    for (int t = 0; t < 48; ++t) tab[RT_ETOT + t] = occ_E_tot(*P, t >> 4, t & 15);
+    for (int t = 0; t < 32; ++t) tab[RT_EXP2 + t] = h_exp2_tab[t];
+    const uint64_t lut = tile_code_lut(*P);
+    std::vector<uint8_t> cvox(N);
+    std::vector<double> pairop(N);
+    long long oriented = 0;
+    for (long long s = 0; s < N; ++s) {
+        const unsigned code = (unsigned)(lut >> (4 * (vox[s] & 15))) & 15u;
+        cvox[s] = (uint8_t)((vox[s] & 0xF0) | code);
+        pairop[s] = tile_pairop(*P, code, T[s], v[s].z);
+        if (code == TC_EMPTY && !(v[s].x == 0.0 && v[s].y == 0.0 && v[s].z == 1.0)) ++oriented;
+    }
+    for (int i = 0; i < L; ++i)
+        for (int j = 0; j < L; ++j)
+            for (int k = 0; k < L; ++k) {
+                const long long s = g.idx(i, j, k);
+                general[s] = site_rate_sum(g, *P, i, j, k, nullptr);
+                uint64_t w = 0;
+                for (int o = 0; o < 14; ++o) {
+                    const int ni = i + CET_NB_DI(o), nj = j + CET_NB_DJ(o), nk = k + CET_NB_DK(o);
+                    if (ni < 0 || ni >= L || nj < 0 || nj >= L || nk < 0 || nk >= L) continue;      // outside: code 0
+                    w |= (uint64_t)(cvox[g.idx(ni, nj, nk)] & 15u) << (4 * o);
+                }
+                const unsigned c = cvox[s];
+                double T_self = 1.0, T_m = 1.0, T_p = 1.0;
+                if ((c & 15u) == TC_EMPTY) {
+                    T_self = pairop[s];
+                    T_m = k > 0 ? ((cvox[s - 1] & 15u) == TC_EMPTY ? pairop[s - 1] : T[s - 1]) : T_self;
+                    T_p = k < L - 1 ? ((cvox[s + 1] & 15u) == TC_EMPTY ? pairop[s + 1] : T[s + 1]) : T_self;
+                } else {
+                    T_self = T[s];
+                }
+                const TilePrep q = tile_site_prep(*P, tab.data(), w, c, T_self, T_m, T_p);
+                double sum = q.sum0;
+                for (int o = 0; o < 14; ++o)
+                    if (q.pm >> (4 * o) & 1u) {
+                        const long long t = s + CET_NB_DI(o) * LL + CET_NB_DJ(o) * L + CET_NB_DK(o);
+                        sum += tile_pair_rate(*P, tab.data(), q.is_emp, q.A, q.B, pairop[t]);
+                    }
+                tile[s] = sum;
+            }
+    return oriented;
+}

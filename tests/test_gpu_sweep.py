@@ -1,5 +1,7 @@
-"""GPU: synchronous-sublattice sweeps (csrc/sweep.cu) — invariants, determinism and level-3
-parity (trajectory observables against the serial oracle within statistical bounds)."""
+"""GPU: synchronous-sublattice sweeps (csrc/sweep.cu, csrc/sweep_tile.cu) — invariants, determinism
+and level-3 parity (trajectory observables against the serial oracle within statistical bounds).
+FUSED = the TMA-staged tile kernel, NO_TMA = the same kernel with cooperative tile loads,
+GATHER = the kernels of the first design (Context.debug_flags)."""
 import numpy as np
 import pytest
 
@@ -13,25 +15,30 @@ def _sweep_params(cet, seed, L, eps=0.02, p_max=0.25, defect_fraction=0.0, therm
     return sp
 
 
-def _setup(cet, L, seed=3, c=0.1):
+FUSED, NO_TMA, GATHER = 0, 1, 2
+
+
+def _setup(cet, L, seed=3, c=0.1, flags=FUSED):
     from cetkmc import _synth
     from cetkmc._config import rate_params
     packed, th, ph, T = _synth.half_grown(L, seed=seed, grain=4)
     ctx = cet.Context(L=L)
+    ctx.debug_flags(flags)
     ctx.set_rate_params(rate_params(c))
     st, df = _synth.unpack(packed)
     ctx.upload(state=st, theta=th, phi=ph, T=T, defects=df)
     return ctx, st, th, ph, T, df
 
 
-def test_sweep_is_deterministic_and_consistent(cet):
-    L = 40
+@pytest.mark.parametrize("L,flags", [(40, FUSED), (64, FUSED), (40, GATHER)])
+def test_sweep_is_deterministic_and_consistent(cet, L, flags):
     outs = []
     for _ in range(2):
-        ctx, st, th, ph, T, df = _setup(cet, L)
+        ctx, st, th, ph, T, df = _setup(cet, L, flags=flags)
         res = ctx.sweep_run(12, _sweep_params(cet, 11, L, defect_fraction=0.01), None)
         outs.append((res, ctx.download(state=True, theta=True, phi=True), ctx.counts()))
-        assert ctx.nst_mismatches() == 0          # the incrementally patched neighbour cache equals a fresh gather
+        if flags == GATHER:
+            assert ctx.nst_mismatches() == 0      # the incrementally patched neighbour cache equals a fresh gather
         ctx.close()
     (r1, f1, c1), (r2, f2, c2) = outs
     assert r1 == r2 and r1["events_applied"] > 0 and r1["events_applied"] <= r1["events_fired"]
@@ -47,20 +54,69 @@ def test_sweep_is_deterministic_and_consistent(cet):
     assert c1.sum() == L ** 3 and np.array_equal(c1, c2)
 
 
-def test_first_sweep_measures_only(cet, oracle):
-    """tau starts at 0: the first sweep evaluates every rate and fires nothing; its total equals
-    the oracle's total rate."""
+@pytest.mark.parametrize("flags", [FUSED, GATHER])
+def test_first_sweep_is_primed(cet, oracle, flags):
+    """A fresh clock (tau = 0) is primed by a pass that only measures the total rate, so the first
+    counted sweep is a real one: it fires about events_per_sweep events, advances time by
+    tau = events_per_sweep / R_total, and the total it reports equals the oracle's total rate of the
+    initial lattice.  The expected number of fired sites is sum(1 - exp(-R tau))."""
     L = 24
-    ctx, st, th, ph, T, df = _setup(cet, L)
-    res = ctx.sweep_run(1, _sweep_params(cet, 1, L), None)
-    assert res["events_fired"] == 0 and res["time"] == 0.0
+    ctx, st, th, ph, T, df = _setup(cet, L, flags=flags)
+    sp = _sweep_params(cet, 1, L, eps=0.01, p_max=0.1)
+    res = ctx.sweep_run(1, sp, None)
     ev = oracle.event_rates(st, th, ph, T, df, L, oracle.make_params(0.1))
-    assert abs(res["last_total_rate"] - oracle.pysum(ev["rate"])) <= 1e-11 * res["last_total_rate"]
-    o_sr, o_dep, _, _ = oracle.site_rates(st, th, ph, T, df, L, oracle.make_params(0.1))
-    o_sr[L - 1] += np.nan_to_num(o_dep)
-    assert abs(res["last_max_rate"] - o_sr.max()) <= 1e-12 * o_sr.max()
+    total = oracle.pysum(ev["rate"])
+    o_sr0, o_dep0, _, _ = oracle.site_rates(st, th, ph, T, df, L, oracle.make_params(0.1))
+    R = o_sr0.copy(); R[L - 1] += np.nan_to_num(o_dep0)
+    tau = min(sp.events_per_sweep / total, -np.log1p(-sp.p_max) / R.max())
+    assert abs(res["time"] - tau) <= 1e-11 * tau and res["sweep_index"] == 1
+    expect = float(np.sum(-np.expm1(-R * tau)))
+    assert abs(res["events_fired"] - expect) <= 5 * np.sqrt(expect) + 1
+    assert 0 < res["events_applied"] <= res["events_fired"]
+    assert abs(res["last_total_rate"] - total) <= 1e-11 * total
+    assert abs(res["last_max_rate"] - R.max()) <= 1e-12 * R.max()
     assert res["last_tau"] > 0
     ctx.close()
+
+
+@pytest.mark.parametrize("L", [64, 80])
+def test_tma_and_cooperative_tile_loads_agree(cet, L):
+    """The fused kernel with TMA-staged tiles and with cooperative loads runs the same trajectory bit
+    for bit (same Philox keys, same arithmetic): lattice, counters and resident rates."""
+    from cetkmc._config import thermal_params
+    outs = []
+    for flags in (FUSED, NO_TMA):
+        ctx, st, th, ph, T, df = _setup(cet, L, flags=flags)
+        res = ctx.sweep_run(7, _sweep_params(cet, 5, L, eps=0.01, p_max=0.2, defect_fraction=0.01, thermal_every=3),
+                            thermal_params(1e-6, nan_to_num=True))
+        outs.append((res, ctx.download(state=True, theta=True, phi=True, T=True), ctx.rates_download()))
+        ctx.close()
+    (r1, f1, (s1, d1)), (r2, f2, (s2, d2)) = outs
+    assert r1 == r2 and r1["events_applied"] > 100
+    for k in f1:
+        np.testing.assert_array_equal(f1[k], f2[k])
+    np.testing.assert_array_equal(s1, s2)
+    np.testing.assert_array_equal(d1, d2)
+
+
+def test_oriented_empty_sites_take_the_gather_path(cet):
+    """Empty sites that carry an orientation (never produced by the reference, but legal input)
+    break the invariant the fused kernel's pair operands rely on: the sweep detects it on the device
+    and runs the general gather kernels, whose rates stay equal to a dense rebuild."""
+    L = 32
+    ctx, st, th, ph, T, df = _setup(cet, L)
+    rng = np.random.default_rng(0)
+    th2 = np.where(st == 0, rng.uniform(0, np.pi, st.shape), th)
+    ctx.upload(theta=th2)
+    res = ctx.sweep_run(4, _sweep_params(cet, 2, L, eps=0.01, p_max=0.2), None)
+    assert res["events_applied"] > 50
+    assert ctx.nst_mismatches() == 0          # only the gather path maintains (and validates) the cache
+    sr1, dr1 = ctx.rates_download()
+    ctx.rates_build()
+    sr2, dr2 = ctx.rates_download()
+    ctx.close()
+    np.testing.assert_array_equal(sr1, sr2)
+    np.testing.assert_array_equal(dr1, dr2)
 
 
 def test_diffusion_only_conserves_atoms(cet):
@@ -132,18 +188,20 @@ def test_level3_observables_vs_serial_oracle(cet, oracle):
     assert np.all(np.abs(mo - mg) <= tol), (mo, mg, tol)
 
 
-def test_resident_rates_equal_rebuild_after_sweeps(cet):
+@pytest.mark.parametrize("L,flags", [(36, FUSED), (64, FUSED), (96, FUSED), (36, GATHER)])
+def test_resident_rates_equal_rebuild_after_sweeps(cet, L, flags):
     """Neighbour-rate refresh invariant: after N sweeps (thermal steps and defect injection
-    included) the resident rate sums and the cached neighbour words equal a dense rebuild bit for
-    bit."""
+    included) the resident rate sums equal a dense rebuild by the gather kernel of rates.cu bit for
+    bit — for the fused tile kernel this also pins its class-code / pair-operand arithmetic and its
+    incrementally maintained tile state to the per-event code."""
     from cetkmc._config import thermal_params
-    L = 36
-    ctx, st, th, ph, T, df = _setup(cet, L)
+    ctx, st, th, ph, T, df = _setup(cet, L, flags=flags)
     res = ctx.sweep_run(9, _sweep_params(cet, 21, L, eps=0.01, p_max=0.2, defect_fraction=0.02, thermal_every=4),
                         thermal_params(1e-6, nan_to_num=True))
     assert res["events_applied"] > 100 and res["sites_refreshed"] > res["events_applied"]
-    sr1, dr1 = ctx.rates_download()          # resident arrays as the sweeps left them
-    assert ctx.nst_mismatches() == 0
+    sr1, dr1 = ctx.rates_download()          # resident arrays as the sweeps left them (pending refreshes flushed)
+    if flags == GATHER:
+        assert ctx.nst_mismatches() == 0
     ctx.rates_build()                        # dense rebuild from the lattice
     sr2, dr2 = ctx.rates_download()
     ctx.close()

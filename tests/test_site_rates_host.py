@@ -73,3 +73,33 @@ def test_neighbour_class_words(hostsim):
                     inb = 0 <= ni < L and 0 <= nj < L and 0 <= nk < L
                     w |= (code[int(st[ni, nj, nk])] if inb else 8) << (4 * o)
                 assert int(out[(i * L + j) * L + k]) == w, (i, j, k)
+
+
+@pytest.mark.parametrize("name", sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "rates_*.npz"))))
+def test_tile_evaluation_equals_per_event_code(hostsim, name):
+    """The fused sweep kernel evaluates a site from class codes + one pair operand per neighbour
+    (csrc/tile_state.cuh).  On the reference's lattices (empty sites carry no orientation) that must
+    give the bits of the per-event code (site_rate_sum), which the fixtures pin to the reference."""
+    from cetkmc._config import rate_params
+    g = golden(name)
+    L = g["state"].shape[0]
+    P = rate_params(float(g["impurity_c"]))
+    st = g["state"].astype(np.uint8)
+    rng = np.random.default_rng(L)
+    st = np.where(rng.random(st.shape) < 0.03, 5, st).astype(np.uint8)       # a few sites of an unknown species
+    vox = (st | (g["defects"].astype(np.uint8) << 4)).ravel()
+    th, ph, T = (np.ascontiguousarray(g[k], dtype=np.float64).copy() for k in ("theta", "phi", "T"))
+    canonical = name != "rates_general9.npz"
+    if canonical:
+        th[st == 0] = 0.0
+        ph[st == 0] = 0.0
+    tile = np.zeros(L ** 3); gen = np.zeros(L ** 3)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    hostsim.hostsim_tile_rates.restype = C.c_longlong
+    oriented = hostsim.hostsim_tile_rates(vp(vox), vp(th), vp(ph), vp(T), L, C.byref(P), vp(tile), vp(gen))
+    if canonical:
+        assert oriented == 0
+        np.testing.assert_array_equal(tile, gen)
+        assert np.count_nonzero(gen) > L ** 3 // 4
+    else:
+        assert oriented > 0                          # the invariant check sends such lattices to the gather kernels
