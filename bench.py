@@ -168,8 +168,7 @@ def main():
     ap.add_argument("--L", type=int, default=L_BENCH, help="sites per edge in a plane and planes per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--gather", action="store_true", help="first-design gather kernels instead of the fused tile kernel (A/B)")
-    ap.add_argument("--no-tma", action="store_true", help="fused kernel with cooperative tile loads (A/B)")
+    ap.add_argument("--debug-flags", type=int, default=0, help="refresh variant for A/B runs (cet_debug_flags)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -200,7 +199,7 @@ def main():
     sites_local, sites_total = L ** 3, L ** 3 * world
 
     ctx = cetkmc.Context(L=L, n0=n0, device=local_rank, i_begin=i_begin, i_end=i_end, halo=halo)
-    ctx.debug_flags((2 if args.gather else 0) | (1 if args.no_tma else 0))
+    ctx.debug_flags(args.debug_flags)
     ctx.set_rate_params(rate_params(0.1))
     ctx.upload_packed(packed)
     ctx.upload(theta=th, phi=ph, T=T)

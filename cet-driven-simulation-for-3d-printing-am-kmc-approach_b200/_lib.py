@@ -432,8 +432,9 @@ class Context:
         return n.value
 
     def debug_flags(self, flags):
-        """Kernel selection of sweep_run (tests / profiling): 1 = tiles staged without TMA, 2 = the
-        gather kernels of the first design instead of the fused tile kernel."""
+        """Refresh-kernel selection of sweep_run (tests / profiling), see cet_debug_flags in cetkmc.h:
+        1 = tiles staged without TMA, 2 = gather refresh of the first design, 4 = per-lane pair loop,
+        8 = dense rebuilds by the gather kernel."""
         check(lib().cet_debug_flags(self._h, int(flags)), "cet_debug_flags")
 
     def sweep_state(self):

@@ -125,9 +125,9 @@ struct cet_ctx {
     int *tile_flag = nullptr;
     bool tile_valid = false;          // cvox / pairop match vox / theta / phi / T / defects / the state ids
     bool emp_canonical = false;       // no empty site carries an orientation (checked by tile_state_ensure)
-    bool stamps_pending = false;      // the last sweep's stamped sites still hold their old rate sums
-    bool tile_attr_set = false;
-    int debug_flags = 0;              // cet_debug_flags: 1 = no TMA (cooperative tile loads), 2 = gather kernels of the first design
+    int tile_blocks[4] = {0, 0, 0, 0}; // resident CTAs per SM of the four tile-kernel variants (0 = not yet queried)
+    int debug_flags = 0;              // cet_debug_flags: 1 = no TMA (cooperative tile loads), 2 = gather refresh of the first design,
+                                      // 4 = tile kernel walks the 14 slots per lane instead of compacting the pairs across the warp
     alignas(64) unsigned char tmap_vox[128];
     alignas(64) unsigned char tmap_po[128];
     const void *tmap_vox_ptr = nullptr, *tmap_po_ptr = nullptr;
@@ -167,7 +167,7 @@ int nst_build(cet_ctx *c, int p_lo, int p_hi);     // rebuild the neighbour-stat
 int nst_ensure(cet_ctx *c);                          // ... of every plane it can be built for, if it is stale
 int sm_count(cet_ctx *c);                            // multiprocessors of the context's device
 // every writer of vox / theta / phi / T / defects other than the tile-aware sweep kernels calls this
-inline void lattice_changed(cet_ctx *c) { c->tile_valid = false; c->rates_valid = false; c->sweep_rates_valid = false; c->stamps_pending = false; }
+inline void lattice_changed(cet_ctx *c) { c->tile_valid = false; c->rates_valid = false; c->sweep_rates_valid = false; }
 enum { PROF_DECIDE = 0, PROF_APPLY = 1, PROF_THERMAL = 2, PROF_RATES = 3, PROF_HALO = 4, PROF_STEP = 5, PROF_PICK = 6,
        PROF_REFRESH = 7, PROF_ALLREDUCE = 8, PROF_BOUNDARY = 9, PROF_KINDS = 10 };
 // RAII span: records an event pair around a launch when profiling is on.

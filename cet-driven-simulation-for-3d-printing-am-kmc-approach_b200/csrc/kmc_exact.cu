@@ -350,7 +350,7 @@ extern "C" int cet_kmc_run(cet_ctx *c, int64_t step0, int64_t n_steps, double de
         kmc_steps_kernel<<<1, KX_THREADS, 0, c->stream>>>(a);
         CET_CUDA(cudaGetLastError());
         c->nst_valid = false;          // the step kernel edits states without maintaining the neighbour cache
-        c->tile_valid = false; c->stamps_pending = false;
+        c->tile_valid = false;
         step += run;
     }
     KmcState out;

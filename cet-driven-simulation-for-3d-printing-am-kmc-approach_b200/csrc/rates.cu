@@ -34,7 +34,6 @@ __global__ void rate_tables_kernel(const cet_rate_params P, double *tab)
 }
 
 struct RateTileArgs;
-int sweep_flush(cet_ctx *c);      // sweep.cu
 template <int MINB>
 __global__ void rates_tile_kernel(const __grid_constant__ RateTileArgs a, int s_lo, int s_hi, unsigned int *queue);
 __global__ void dirty_eval_kernel(const __grid_constant__ RateTileArgs a, const int32_t *list, const unsigned int *n_list,
@@ -411,7 +410,6 @@ int cet_rates_download(cet_ctx *c, double *site_rate, double *dep_rate)
     CET_REQUIRE(c, "cet_rates_download: NULL ctx");
     CET_REQUIRE(c->rates_valid || c->sweep_rates_valid, "cet_rates_download: rates are stale (call cet_rates_build)");
     cet::DeviceGuard dg(c->device);
-    if (int rc = sweep_flush(c)) return rc;          // the fused sweep path refreshes lazily
     if (site_rate)
         CET_CUDA(cudaMemcpyAsync(site_rate, c->site_rate + c->owned_offset(), (size_t)c->owned_sites() * 8,
                                  cudaMemcpyDeviceToHost, c->stream));

@@ -44,12 +44,10 @@ int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint32_t *stamp, int3
 int comm_sweep_reduce(cet_ctx *c, double *plane_sum, int n, double *max_inout);   // comm.cu
 int comm_halo_exchange(cet_ctx *c, int fields);
 // sweep_tile.cu — the fused tile kernel (refresh + stream) and the arrays it stages
-enum { TM_ALL = 1, TM_STREAM = 2 };
 int tile_state_ensure(cet_ctx *c);
 int tile_state_build(cet_ctx *c, int p_lo, int p_hi);
 int tile_pairop_T_update(cet_ctx *c);
-int tile_pass(cet_ctx *c, int p_lo, int p_hi, int mode, uint64_t seed, uint32_t sweep);
-int tile_parts_per_plane(const cet_ctx *c);
+int tile_pass(cet_ctx *c, int p_lo, int p_hi, bool all);
 int stamp_fill(cet_ctx *c, int p_lo, int p_hi);
 
 struct Record {          // one fired event
@@ -487,7 +485,7 @@ static int sweep_alloc(cet_ctx *c)
         CET_CUDA(cudaMalloc(&c->records, c->cap_fired * sizeof(Record)));
         c->cap_records = c->cap_fired;
     }
-    const int tpp = std::max((int)((c->plane + ST_TILE - 1) / ST_TILE), tile_parts_per_plane(c));
+    const int tpp = (int)((c->plane + ST_TILE - 1) / ST_TILE);
     if (!c->blk_sum) {
         c->n_blk = (int64_t)tpp * c->np;
         CET_CUDA(cudaMalloc(&c->blk_sum, (size_t)c->n_blk * sizeof(double)));
@@ -560,52 +558,48 @@ extern "C" int cet_sweep_set_state(cet_ctx *c, int64_t sweep_index, double tau, 
     CET_CUDA(cudaStreamSynchronize(c->stream));
     c->sweep_index = sweep_index;
     c->last_thermal_index = -1;
-    c->sweep_rates_valid = false; c->stamps_pending = false;
+    c->sweep_rates_valid = false;
     return 0;
 }
 
 namespace cet {
 
-// One sweep.  The fused path (sweep_tile.cu) needs the orientation invariant of tile_state.cuh; the
-// gather path is the first design (stream, pick, apply, stamp scan + list-driven re-evaluation).
+// One sweep.  tiled: the rate sums are kept current by the TMA tile kernel (sweep_tile.cu), which needs
+// the orientation invariant of tile_state.cuh; otherwise by the gather kernels of the first design
+// (stamp scan + list-driven re-evaluation, rates.cu).  Stream, pick and apply are the same either
+// way, so both variants run the same trajectory bit for bit.
 // count == false is the priming pass of a fresh clock: tau is still 0, nothing can fire, and the pass
 // only measures the totals that give the first real sweep its interval.
-static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_params *tp, const SlabRanges &R, bool fused,
+static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_params *tp, const SlabRanges &R, bool tiled,
                       bool count)
 {
     const int n_eval = R.eval_hi - R.eval_lo;
     const int i_off = (int)(c->i_begin - c->halo);
     const int top_plane = (int)(c->n0 - 1 - i_off);
+    const int tpp = (int)((c->plane + ST_TILE - 1) / ST_TILE);
     double *max_slot = c->plane_sum + c->n0;      // plane_sum[n0] holds the running max
     ProfScope step_scope(c, PROF_STEP);
     if (sp->thermal_every > 0 && c->sweep_index % sp->thermal_every == 0 && c->last_thermal_index != c->sweep_index) {
         if (int rc = thermal_cet_step(c, tp, &c->sweep->terminated)) return rc;      // clears sweep_rates_valid
         if (c->world > 1) if (int rc = comm_halo_exchange(c, 4)) return rc;
-        if (fused) if (int rc = tile_pairop_T_update(c)) return rc;
+        if (tiled) if (int rc = tile_pairop_T_update(c)) return rc;
         c->last_thermal_index = c->sweep_index;
     }
-    sweep_reset_kernel<<<1, 1, 0, c->stream>>>(c->sweep, max_slot);
-    CET_CUDA(cudaMemsetAsync(c->plane_sum, 0, (size_t)c->n0 * sizeof(double), c->stream));
-    int parts;
-    if (fused) {
-        // refresh (the stamped sites of the previous sweep, or every site after a thermal step / upload)
-        // and the fire test of this sweep in one pass
-        const bool all = !c->sweep_rates_valid;
-        {
-            ProfScope ps(c, all ? PROF_RATES : PROF_DECIDE);
-            if (int rc = tile_pass(c, R.eval_lo, R.eval_hi, (all ? TM_ALL : 0) | TM_STREAM, sp->seed, (uint32_t)c->sweep_index))
-                return rc;
+    if (!c->sweep_rates_valid) {                     // new lattice, new T or new parameters: dense rebuild
+        if (tiled && !(c->debug_flags & 8)) {
+            ProfScope ps(c, PROF_RATES);
+            if (int rc = tile_pass(c, R.eval_lo, R.eval_hi, true)) return rc;
+        } else {
+            if (tiled) c->nst_valid = false;         // nobody maintains the neighbour cache on the tile path
+            if (int rc = nst_ensure(c)) return rc;
+            if (int rc = rates_rows(c, R.eval_lo, R.eval_hi)) return rc;
         }
         c->sweep_rates_valid = true;
-        CET_CUDA(cudaMemsetAsync(c->stamp, 0, (size_t)c->nloc / 8 + 8, c->stream));      // consumed; apply sets the next ones
-        parts = tile_parts_per_plane(c);
-    } else {
-        if (!c->sweep_rates_valid) {                 // new lattice, new T or new parameters: dense rebuild
-            if (int rc = rates_rows(c, R.eval_lo, R.eval_hi)) return rc;
-            c->sweep_rates_valid = true;
-        }
-        CET_CUDA(cudaMemsetAsync(c->stamp, 0, (size_t)c->nloc / 8 + 8, c->stream));      // stamp bitmap of this sweep
-        const int tpp = (int)((c->plane + ST_TILE - 1) / ST_TILE);
+    }
+    CET_CUDA(cudaMemsetAsync(c->stamp, 0, (size_t)c->nloc / 8 + 8, c->stream));      // stamp bitmap of this sweep
+    sweep_reset_kernel<<<1, 1, 0, c->stream>>>(c->sweep, max_slot);
+    CET_CUDA(cudaMemsetAsync(c->plane_sum, 0, (size_t)c->n0 * sizeof(double), c->stream));
+    {
         StreamArgs a;
         a.site_rate = c->site_rate; a.dep_rate = c->dep_rate; a.ss = c->sweep;
         a.fired = c->fired; a.cap_fired = (unsigned int)c->cap_fired;
@@ -616,11 +610,10 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
         a.seed = sp->seed; a.sweep = (uint32_t)c->sweep_index;
         ProfScope ps(c, PROF_DECIDE);
         sweep_stream_kernel<<<n_eval * tpp, ST_THREADS, 0, c->stream>>>(a);
-        parts = tpp;
     }
     CET_CUDA(cudaGetLastError());
     sweep_plane_reduce_kernel<<<(n_eval + 3) / 4, 128, 0, c->stream>>>(
-        c->blk_sum, c->blk_max, parts, n_eval, i_off + R.eval_lo, (int)c->i_begin, (int)c->i_end,
+        c->blk_sum, c->blk_max, tpp, n_eval, i_off + R.eval_lo, (int)c->i_begin, (int)c->i_end,
         c->plane_sum, max_slot);
     CET_CUDA(cudaGetLastError());
     const int sparse_grid = sm_count(c) * 32;
@@ -643,14 +636,17 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
         b.c_lo = R.claim_lo; b.c_hi = R.claim_hi; b.own_lo = R.own_lo; b.own_hi = R.own_hi;
         b.seed = sp->seed; b.sweep = (uint32_t)c->sweep_index;
         b.defect_fraction = sp->defect_fraction;
-        b.cvox = fused ? c->cvox : nullptr; b.pairop = c->pairop; b.T = c->T; b.tlut = tile_code_lut(c->rp);
+        b.cvox = tiled ? c->cvox : nullptr; b.pairop = c->pairop; b.T = c->T; b.tlut = tile_code_lut(c->rp);
         ProfScope ps(c, PROF_APPLY);
         sweep_apply_kernel<<<sparse_grid, 128, 0, c->stream>>>(b);
     }
     CET_CUDA(cudaGetLastError());
-    if (!fused) {
+    if (!tiled) {
         ProfScope ps(c, PROF_REFRESH);
         if (int rc = rates_rows_dirty(c, R.eval_lo, R.eval_hi, c->stamp, c->dirty, &c->sweep->n_dirty)) return rc;
+    } else if (c->world == 1) {
+        ProfScope ps(c, PROF_REFRESH);
+        if (int rc = tile_pass(c, R.eval_lo, R.eval_hi, false)) return rc;
     }
     // the totals are only needed for the next tau: reduce them here, next to the halo exchange, so
     // that a sweep has one inter-rank synchronisation point instead of two
@@ -661,23 +657,28 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
     sweep_finalize_kernel<<<1, 256, 0, c->stream>>>(c->sweep, c->plane_sum, (int)c->n0, max_slot,
                                                     sp->events_per_sweep, sp->p_max);
     CET_CUDA(cudaGetLastError());
-    if (c->world > 1 && count) {
+    if (c->world > 1) {
         {
             ProfScope ps(c, PROF_HALO);
             if (int rc = comm_halo_exchange(c, 1 | 2)) return rc;
         }
-        ProfScope pb(c, PROF_BOUNDARY);
         // The ghost planes now hold the owners' lattice.  Events this slab could not resolve
         // (write set reaching beyond ghost depth 2) may have changed ghost planes that the two
         // outermost owned planes read, so the evaluated ghost planes and those two owned planes on
-        // each cut face are re-evaluated: densely here (gather path), or by stamping them for the
-        // refresh of the next fused pass.
-        if (fused) {
-            if (int rc = tile_state_build(c, 0, R.own_lo)) return rc;
-            if (int rc = tile_state_build(c, R.own_hi, (int)c->np)) return rc;
-            if (R.own_lo > R.eval_lo) if (int rc = stamp_fill(c, R.eval_lo, R.own_lo + 2)) return rc;
-            if (R.eval_hi > R.own_hi) if (int rc = stamp_fill(c, R.own_hi - 2, R.eval_hi)) return rc;
+        // each cut face are re-evaluated: densely (gather path), or by stamping them into the one
+        // refresh pass of the sweep (tile path).
+        if (tiled) {
+            {
+                ProfScope pb(c, PROF_BOUNDARY);
+                if (int rc = tile_state_build(c, 0, R.own_lo)) return rc;
+                if (int rc = tile_state_build(c, R.own_hi, (int)c->np)) return rc;
+                if (R.own_lo > R.eval_lo) if (int rc = stamp_fill(c, R.eval_lo, R.own_lo + 2)) return rc;
+                if (R.eval_hi > R.own_hi) if (int rc = stamp_fill(c, R.own_hi - 2, R.eval_hi)) return rc;
+            }
+            ProfScope ps(c, PROF_REFRESH);
+            if (int rc = tile_pass(c, R.eval_lo, R.eval_hi, false)) return rc;
         } else {
+            ProfScope pb(c, PROF_BOUNDARY);
             c->nst_valid = true;       // the exchange marked the whole cache stale; only the planes rebuilt below are
             if (R.own_lo > R.eval_lo) {
                 if (int rc = nst_build(c, R.eval_lo, R.own_lo + 2)) return rc;
@@ -690,18 +691,6 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
         }
     }
     if (count) c->sweep_index++;
-    return 0;
-}
-
-// Bring the resident rate sums up to date with the lattice (the fused path refreshes the sites an
-// event touched at the START of the next sweep): one refresh-only pass over the stamped sites.
-int sweep_flush(cet_ctx *c)
-{
-    if (!c->stamps_pending || !c->sweep_rates_valid || !c->tile_valid) return 0;
-    const SlabRanges R = slab_ranges(c);
-    if (int rc = tile_pass(c, R.eval_lo, R.eval_hi, 0, 0, 0)) return rc;
-    CET_CUDA(cudaMemsetAsync(c->stamp, 0, (size_t)c->nloc / 8 + 8, c->stream));
-    c->stamps_pending = false;
     return 0;
 }
 
@@ -727,32 +716,29 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
     CET_CUDA(cudaMemcpyAsync(&before, c->sweep, sizeof(before), cudaMemcpyDeviceToHost, c->stream));
     CET_CUDA(cudaStreamSynchronize(c->stream));
 
-    // Which kernels: the fused tile pass when no empty site carries an orientation (the reference's
-    // invariant, checked here on the device), the gather kernels otherwise.  A change of path drops
-    // the state only the other path maintains.
-    bool fused = !(c->debug_flags & 2);
-    if (fused) {
-        if (!c->tile_valid) { c->sweep_rates_valid = false; c->stamps_pending = false; }
+    // Which refresh: the TMA tile kernel when no empty site carries an orientation (the reference's
+    // invariant, checked here on the device), the gather kernels otherwise.  A change of variant
+    // drops the state only the other one maintains.
+    bool tiled = !(c->debug_flags & 2);
+    if (tiled) {
         if (int rc = tile_state_ensure(c)) return rc;
-        fused = c->emp_canonical;
+        tiled = c->emp_canonical;
     }
     if (c->world > 1) {                      // every slab must take the same path
-        double f = fused ? 0.0 : 1.0;
+        double f = tiled ? 0.0 : 1.0;
         if (int rc = cet_allreduce_f64(c, &f, 1, 1)) return rc;
-        fused = f == 0.0;
+        tiled = f == 0.0;
     }
-    if (fused) {
-        c->nst_valid = false;                // the fused path keeps no neighbour cache
+    if (tiled) {
+        c->nst_valid = false;                // the tile path keeps no neighbour cache
     } else {
-        if (c->stamps_pending) { c->sweep_rates_valid = false; c->stamps_pending = false; }
         c->tile_valid = false;               // the gather path's apply does not maintain cvox / pairop
         if (int rc = nst_ensure(c)) return rc;
     }
     if (n_sweeps > 0 && before.tau == 0.0 && !before.terminated)
-        if (int rc = sweep_once(c, sp, tp, R, fused, false)) return rc;
+        if (int rc = sweep_once(c, sp, tp, R, tiled, false)) return rc;
     for (int64_t n = 0; n < n_sweeps; ++n)
-        if (int rc = sweep_once(c, sp, tp, R, fused, true)) return rc;
-    if (fused && n_sweeps > 0) c->stamps_pending = true;
+        if (int rc = sweep_once(c, sp, tp, R, tiled, true)) return rc;
     c->rates_valid = false;          // the BKL sum hierarchy is not maintained by the sweeps
     SweepState after;
     CET_CUDA(cudaMemcpyAsync(&after, c->sweep, sizeof(after), cudaMemcpyDeviceToHost, c->stream));

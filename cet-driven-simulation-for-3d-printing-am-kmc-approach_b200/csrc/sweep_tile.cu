@@ -1,19 +1,17 @@
-// sweep_tile.cu — the fused tile kernel of the synchronous-sublattice sweep.
+// sweep_tile.cu — the tile kernel that keeps the resident rate sums current: neighbour-rate refresh
+// after a sweep's events, and the dense rebuild after a thermal step.
 //
-// One pass over the lattice does, per 8 x 8 x 32 tile of sites,
-//   refresh : re-evaluate the rate sum of every site whose stamp bit is set (the sites an event of the
-//             previous sweep changed, and their neighbours) — or of every site after a thermal step —
-//             from a tile of cvox + pairop (tile_state.cuh) staged in shared memory with its halo of 2
-//             by two 3-D TMA loads (cp.async.bulk.tensor), double-buffered so that the loads of the
-//             next tile run under the arithmetic of the current one;
-//   stream  : one fire test per site against its (now current) rate sum, p = 1 - exp(-R tau), with a
-//             Philox4x32-10 block per 4 sites keyed by (seed, sweep, global plane, row band, k);
-//             fired sites are appended to the sweep's list; per-(plane, tile) partial sums and maxima
-//             of R feed the next time increment in a fixed order.
-// This replaces three kernels and one cache of the first design (stream, stamp scan, list-driven
-// re-evaluation with ~15 gathered DRAM sectors per site, and the 8-byte neighbour-class word the
-// gathers maintained): neighbour states and pair operands now come from shared memory, and DRAM
-// sees one streaming read of cvox (1 B), pairop (8 B) and the rate sums (8 B) per site.
+// Per 4 x 8 x 32 tile of sites a CTA stages cvox + pairop (tile_state.cuh) with their halo of 2 in
+// shared memory by two 3-D TMA loads (cp.async.bulk.tensor, completion on an mbarrier) and then
+// re-evaluates the rate sum of every site whose stamp bit is set (the sites an event changed, and
+// their neighbours) — or of every site — reading neighbour classes and pair operands from the tile.
+// While the loads are in flight one warp turns the tile's stamp words into a list of its stamped
+// sites.  Several CTAs share an SM, so one tile's loads run under another tile's arithmetic.
+//
+// This replaces the list-driven gather refresh of the first design (stamp scan + re-evaluation that
+// touched ~15 DRAM sectors per refreshed site, 5.3 GB per sweep at 512^3 for 0.35 GB of information,
+// plus an 8-byte neighbour-class cache per site that the gathers maintained): DRAM now sees one
+// streaming read of cvox (1 B) and pairop (8 B) per site and the halo re-reads stay in L2.
 //
 // The pair arithmetic is the per-event code of site_rates.cuh (att_pair_rate_E / diff_pair_rate),
 // the per-site half is tile_site_prep (tile_state.cuh), and a site adds its pairs in slot order, so
@@ -21,7 +19,6 @@
 #include <cuda.h>
 #include <algorithm>
 #include "ctx.cuh"
-#include "philox.cuh"
 #include "reduce.cuh"
 #include "tile_state.cuh"
 
@@ -36,20 +33,21 @@ struct TileWarpSmem {
     double A[32], B[32];
     uint32_t desc[TL_PAIRS];             // staged pairop index of the neighbour | owner lane << 14
 };
+// EVAL 0: pairs compacted across the warp (TileWarpSmem scratch); EVAL 1: every lane walks its own 14 slots
+template <int EVAL>
 struct TileSmem {
-    double po[2][TL_HI * TL_HJ * TL_PK];         // 128-byte aligned TMA destinations first
-    uint8_t vx[2][TL_VBYTES];
+    double po[TL_HI * TL_HJ * TL_PK];            // 128-byte aligned TMA destinations first
+    uint8_t vx[TL_VBYTES];
     double tab[RT_TABLE_DOUBLES];
-    TileWarpSmem w[TL_WARPS];
+    TileWarpSmem w[EVAL == 0 ? TL_WARPS : 1];
     uint16_t dlist[TL_SITES];
     int dp[16];                                  // staged pairop offset of neighbour slot o
-    unsigned long long bar[2];
+    unsigned long long bar;
     unsigned int n_dirty;
 };
-static_assert(sizeof(TileSmem) + 1024 <= 227 * 1024, "TileSmem exceeds the shared memory of an SM");
 static_assert((TL_PBYTES % 128) == 0 && (TL_VBYTES % 128) == 0, "TMA destinations must stay 128-byte aligned");
 
-enum { TM_ALL = 1, TM_STREAM = 2 };
+enum { TM_ALL = 1 };
 
 struct TileArgs {
     const uint8_t *cvox;
@@ -57,9 +55,6 @@ struct TileArgs {
     double *site_rate, *dep_rate;
     const uint32_t *stamp;
     SweepState *ss;
-    int32_t *fired;
-    unsigned int cap_fired;
-    double *blk_sum, *blk_max;
     const double *tab;
     cet_rate_params P;
     int L, n0, np, i_off;
@@ -67,8 +62,6 @@ struct TileArgs {
     int top_plane;               // local plane of the global top plane, or -1
     int njb, nkb, n_tiles;
     int mode;
-    uint64_t seed;
-    uint32_t sweep;
 };
 
 // ---- mbarrier / TMA (PTX ISA 8.x; sm_90+) ------------------------------------------------------
@@ -104,26 +97,21 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         : "memory");
 }
 
-// The rare exact fire test of a site whose 32-bit digit passed the pre-filter (out of line).
-__device__ __noinline__ bool tile_fire_exact(double x, double d, uint64_t seed, uint64_t gsite, uint32_t sweep)
-{
-    const double p32 = -expm1(-x) * 4294967296.0;
-    const double f = floor(p32);
-    if (d != f) return d < f;
-    double u_rest, unused;                              // leading digit ties: the rest of the uniform decides
-    philox_u2(seed, gsite, sweep, STREAM_FIRE_REST, &u_rest, &unused);
-    return u_rest < p32 - f;
-}
+// What a lane knows about its site before the pair phase.
+struct TileSite {
+    TilePrep q;
+    double T_self;
+    int pidx, s;
+};
 
-// Evaluate one site per lane (all 32 lanes call).  sv / sp: the staged cvox / pairop tile.
-__device__ __forceinline__ void tile_eval(const TileArgs &a, const TileSmem &sm, TileWarpSmem &ws, const uint8_t *sv,
-                                          const double *sp, int li, int lj, int lk, int p, int j, int k, bool active)
+// Per-site half: class codes of the 14 neighbours from the staged tile, temperatures, tile_site_prep.
+__device__ __forceinline__ TileSite tile_site(const TileArgs &a, const double *tab, const uint8_t *sv, const double *sp, int li,
+                                              int lj, int lk, int p, int j, int k, bool active)
 {
-    const cet_rate_params &P = a.P;
-    const int lane = threadIdx.x & 31;
+    TileSite r;
     const int vidx = ((li + 2) * TL_HJ + (lj + 2)) * TL_VK + lk + TL_VK0;
-    const int pidx = ((li + 2) * TL_HJ + (lj + 2)) * TL_PK + lk + TL_PK0;
-    const int s = (p * a.L + j) * a.L + k;
+    r.pidx = ((li + 2) * TL_HJ + (lj + 2)) * TL_PK + lk + TL_PK0;
+    r.s = (p * a.L + j) * a.L + k;
     unsigned c = 0;
     uint32_t wlo = 0, whi = 0;
     double T_self = 1.0, T_m = 1.0, T_p = 1.0;
@@ -137,27 +125,47 @@ __device__ __forceinline__ void tile_eval(const TileArgs &a, const TileSmem &sm,
             whi |= ((unsigned)sv[vidx + (CET_NB_DI(o) * TL_HJ + CET_NB_DJ(o)) * TL_VK + CET_NB_DK(o)] & 15u) << (4 * (o - 8));
         const unsigned code = c & 15u;
         if (code == TC_EMPTY) {
-            T_self = sp[pidx];                                       // an empty site's pairop is its temperature
+            T_self = sp[r.pidx];                                     // an empty site's pairop is its temperature
             T_m = T_self; T_p = T_self;
             if ((wlo | whi) & 0x11111111u) {                         // an occupied neighbour: grad_z is needed (:151-153)
-                if (k > 0) T_m = (sv[vidx - 1] & 15u) == TC_EMPTY ? sp[pidx - 1] : a.T[s - 1];
-                if (k < a.L - 1) T_p = (sv[vidx + 1] & 15u) == TC_EMPTY ? sp[pidx + 1] : a.T[s + 1];
+                if (k > 0) T_m = (sv[vidx - 1] & 15u) == TC_EMPTY ? sp[r.pidx - 1] : a.T[r.s - 1];
+                if (k < a.L - 1) T_p = (sv[vidx + 1] & 15u) == TC_EMPTY ? sp[r.pidx + 1] : a.T[r.s + 1];
             }
         } else if ((code & 1u) && code != TC_DEFECT) {
-            T_self = a.T[s];
+            T_self = a.T[r.s];
         }
     }
     const uint64_t w = (uint64_t)wlo | ((uint64_t)whi << 32);
-    const TilePrep q = tile_site_prep(P, sm.tab, w, active ? c : 0u, T_self, T_m, T_p);
-    const uint64_t pm = q.pm;
-    const bool is_emp = q.is_emp;
-    if (pm) { ws.A[lane] = q.A; ws.B[lane] = q.B; }
-    const int cnt = popc64(pm);
+    r.q = tile_site_prep(a.P, tab, w, active ? c : 0u, T_self, T_m, T_p);
+    r.T_self = T_self;
+    return r;
+}
 
+__device__ __forceinline__ void tile_store(const TileArgs &a, const TileSite &t, double sum, int p, int j, int k)
+{
+    a.site_rate[t.s] = sum;
+    if (p == a.top_plane) {                                          // deposition (:55-72)
+        double dep;
+        a.dep_rate[j * a.L + k] = (t.q.is_emp && dep_rate(a.P, t.T_self, &dep)) ? dep : NAN;
+    }
+}
+
+// EVAL 0 — 32 sites per warp, their pairs compacted across the warp (all 32 lanes call).
+__device__ __forceinline__ void tile_eval_packed(const TileArgs &a, const double *tab, const int *dp, TileWarpSmem &ws,
+                                                 const uint8_t *sv, const double *sp, int li, int lj, int lk, int p, int j,
+                                                 int k, bool active)
+{
+    const cet_rate_params &P = a.P;
+    const int lane = threadIdx.x & 31;
+    const TileSite t = tile_site(a, tab, sv, sp, li, lj, lk, p, j, k, active);
+    const uint64_t pm = t.q.pm;
+    const bool is_emp = t.q.is_emp;
+    if (pm) { ws.A[lane] = t.q.A; ws.B[lane] = t.q.B; }
+    const int cnt = popc64(pm);
     // ---- packed counts: attachment pairs in the low half, diffusion pairs in the high half
     const unsigned mine = is_emp ? (unsigned)cnt : (unsigned)cnt << 16;
     const unsigned all = __reduce_add_sync(0xffffffffu, mine);
-    double sum = q.sum0;
+    double sum = t.q.sum0;
     const int npass = all == 0 ? 0 : (((all & 0xFFFFu) + (all >> 16) > (unsigned)TL_PAIRS) ? 2 : 1);
     for (int pass = 0; pass < npass; ++pass) {
         const bool part = npass == 1 || (lane >> 4) == pass;
@@ -165,8 +173,8 @@ __device__ __forceinline__ void tile_eval(const TileArgs &a, const TileSmem &sm,
         unsigned inc = mine_p;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += t;
+            const unsigned u = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += u;
         }
         const unsigned total = __shfl_sync(0xffffffffu, inc, 31), excl = inc - mine_p;
         const int n_att = (int)(total & 0xFFFFu), n_diff = (int)(total >> 16);
@@ -175,16 +183,16 @@ __device__ __forceinline__ void tile_eval(const TileArgs &a, const TileSmem &sm,
         if (part) {
             int pos = start;
             unsigned lo = (unsigned)pm, hi = (unsigned)(pm >> 32);
-            const unsigned base = ((unsigned)lane << 14) + (unsigned)pidx;
+            const unsigned base = ((unsigned)lane << 14) + (unsigned)t.pidx;
             while (lo) {
                 const int b = __ffs(lo) - 1;
                 lo &= lo - 1;
-                ws.desc[pos++] = base + (unsigned)sm.dp[b >> 2];
+                ws.desc[pos++] = base + (unsigned)dp[b >> 2];
             }
             while (hi) {
                 const int b = __ffs(hi) - 1;
                 hi &= hi - 1;
-                ws.desc[pos++] = base + (unsigned)sm.dp[8 + (b >> 2)];
+                ws.desc[pos++] = base + (unsigned)dp[8 + (b >> 2)];
             }
         }
         __syncwarp();
@@ -193,7 +201,7 @@ __device__ __forceinline__ void tile_eval(const TileArgs &a, const TileSmem &sm,
         for (int q0 = lane; q0 < n_att; q0 += 32) {                   // kmc_event_rates.py:135-158
             const unsigned d = ws.desc[q0];
             const int ts = d >> 14;
-            ws.rate[q0] = att_pair_rate_E(P, sp[d & 0x3FFFu], ws.A[ts], ws.B[ts], sm.tab + RT_EXP2);
+            ws.rate[q0] = att_pair_rate_E(P, sp[d & 0x3FFFu], ws.A[ts], ws.B[ts], tab + RT_EXP2);
         }
         for (int q0 = lane; q0 < n_diff; q0 += 32) {                  // :100-109
             const unsigned d = ws.desc[qd0 + q0];
@@ -205,202 +213,138 @@ __device__ __forceinline__ void tile_eval(const TileArgs &a, const TileSmem &sm,
         for (int q0 = 0; q0 < cnt_p; ++q0) sum += ws.rate[start + q0];
         __syncwarp();
     }
-    if (active) {
-        a.site_rate[s] = sum;
-        if (p == a.top_plane) {                                          // deposition (:55-72)
-            double dep;
-            a.dep_rate[j * a.L + k] = (is_emp && dep_rate(P, T_self, &dep)) ? dep : NAN;
-        }
-    }
+    if (active) tile_store(a, t, sum, p, j, k);
 }
 
-template <bool TMA>
-__global__ void __launch_bounds__(TL_THREADS, 1)
-    sweep_tile_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ CUtensorMap tm_vox,
-                      const __grid_constant__ CUtensorMap tm_po)
+// EVAL 1 — every lane walks the 14 slots of its own site; neighbour offsets are immediates.
+__device__ __forceinline__ void tile_eval_serial(const TileArgs &a, const double *tab, const uint8_t *sv, const double *sp, int li,
+                                                 int lj, int lk, int p, int j, int k, bool active)
+{
+    const cet_rate_params &P = a.P;
+    const TileSite t = tile_site(a, tab, sv, sp, li, lj, lk, p, j, k, active);
+    double sum = t.q.sum0;
+    if (__any_sync(0xffffffffu, t.q.pm != 0)) {
+        const bool is_emp = t.q.is_emp;
+        const double A = t.q.A, B = t.q.B;
+        const unsigned lo = (unsigned)t.q.pm, hi = (unsigned)(t.q.pm >> 32);
+#pragma unroll
+        for (int o = 0; o < 14; ++o) {
+            const bool on = ((o < 8 ? lo >> (4 * o) : hi >> (4 * (o - 8))) & 1u) != 0;
+            if (on) {
+                const double op = sp[t.pidx + (CET_NB_DI(o) * TL_HJ + CET_NB_DJ(o)) * TL_PK + CET_NB_DK(o)];
+                sum += is_emp ? att_pair_rate_E(P, op, A, B, tab + RT_EXP2) : diff_pair_rate(P, A, B, op);
+            }
+        }
+    }
+    if (active) tile_store(a, t, sum, p, j, k);
+}
+
+template <bool TMA, int EVAL>
+__global__ void __launch_bounds__(TL_THREADS, EVAL == 0 ? 4 : 5)
+    rates_tile3d_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ CUtensorMap tm_vox,
+                        const __grid_constant__ CUtensorMap tm_po)
 {
     extern __shared__ unsigned char tile_dyn_smem[];
-    TileSmem &sm = *reinterpret_cast<TileSmem *>(tile_dyn_smem + ((1024u - (smem_u32(tile_dyn_smem) & 1023u)) & 1023u));
+    TileSmem<EVAL> &sm = *reinterpret_cast<TileSmem<EVAL> *>(tile_dyn_smem + ((1024u - (smem_u32(tile_dyn_smem) & 1023u)) & 1023u));
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int L = a.L;
 
     for (int q = tid; q < RT_TABLE_DOUBLES; q += TL_THREADS) sm.tab[q] = a.tab[q];
     if (tid < 14) sm.dp[tid] = ((int)c_nb_off[tid][0] * TL_HJ + c_nb_off[tid][1]) * TL_PK + c_nb_off[tid][2];
     if (TMA && tid == 0) {
-        mbar_init(&sm.bar[0], 1);
-        mbar_init(&sm.bar[1], 1);
+        mbar_init(&sm.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     const int tiles_per_iblock = a.njb * a.nkb;
-    auto issue = [&](int t, int buf) {                 // one thread: both boxes of tile t into buffer buf
+    const bool all = (a.mode & TM_ALL) != 0;
+    unsigned int n_staged = 0;                  // tiles staged so far: the mbarrier's phase parity
+    for (int t = (int)blockIdx.x; t < a.n_tiles; t += (int)gridDim.x) {
         const int kb = t % a.nkb, jb = (t / a.nkb) % a.njb, ib = t / tiles_per_iblock;
         const int p0 = a.p_lo + TL_I * ib, j0 = TL_J * jb, k0 = TL_K * kb;
-        mbar_expect_tx(&sm.bar[buf], (unsigned)(TL_VBYTES + TL_PBYTES));
-        tma_load_3d(sm.vx[buf], &tm_vox, &sm.bar[buf], k0 - TL_VK0, j0 - 2, p0 - 2);
-        tma_load_3d(sm.po[buf], &tm_po, &sm.bar[buf], k0 - TL_PK0, j0 - 2, p0 - 2);
-    };
-    if (TMA && tid == 0 && (int)blockIdx.x < a.n_tiles) issue((int)blockIdx.x, 0);
-
-    const double tau = (a.mode & TM_STREAM) ? (a.ss->terminated ? 0.0 : a.ss->tau) : 0.0;
-    unsigned int n_refreshed = 0;
-    int it = 0;
-    for (int t = (int)blockIdx.x; t < a.n_tiles; t += (int)gridDim.x, ++it) {
-        const int buf = TMA ? (it & 1) : 0;
-        const int kb = t % a.nkb, jb = (t / a.nkb) % a.njb, ib = t / tiles_per_iblock;
-        const int p0 = a.p_lo + TL_I * ib, j0 = TL_J * jb, k0 = TL_K * kb;
+        if (TMA && tid == 0) {                                        // both boxes of the tile; one completion barrier
+            mbar_expect_tx(&sm.bar, (unsigned)(TL_VBYTES + TL_PBYTES));
+            tma_load_3d(sm.vx, &tm_vox, &sm.bar, k0 - TL_VK0, j0 - 2, p0 - 2);
+            tma_load_3d(sm.po, &tm_po, &sm.bar, k0 - TL_PK0, j0 - 2, p0 - 2);
+        }
+        // ---- the tile's stamped sites, listed by warp 0 while the loads are in flight
+        if (!all && wid == 0) {
+            constexpr int NH = (TL_I * TL_J + 31) / 32;
+            unsigned bits[NH];
+            int mine = 0;
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                const int row = lane + 32 * h, p = p0 + (row >> 3), j = j0 + (row & 7);
+                unsigned b = 0;
+                if (row < TL_I * TL_J && p < a.p_hi && j < L && k0 < L) {
+                    const int s0 = (p * L + j) * L + k0;
+                    const unsigned w0 = a.stamp[s0 >> 5], w1 = a.stamp[(s0 >> 5) + 1];
+                    b = __funnelshift_r(w0, w1, s0 & 31);
+                    if (L - k0 < 32) b &= (1u << (L - k0)) - 1u;
+                }
+                bits[h] = b;
+                mine += __popc(b);
+            }
+            int inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += u;
+            }
+            int pos = inc - mine;
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                unsigned b = bits[h];
+                const int row = lane + 32 * h;
+                while (b) {
+                    const int e = __ffs(b) - 1;
+                    b &= b - 1;
+                    sm.dlist[pos++] = (uint16_t)(row * TL_K + e);
+                }
+            }
+            if (lane == 31) sm.n_dirty = (unsigned)inc;
+        }
         if (TMA) {
-            if (tid == 0 && t + (int)gridDim.x < a.n_tiles) issue(t + (int)gridDim.x, buf ^ 1);
+            mbar_wait(&sm.bar, n_staged & 1u);
         } else {
             // cooperative loads (lattices whose row stride TMA cannot describe): zero outside the local array
             for (int q = tid; q < TL_VBYTES; q += TL_THREADS) {
                 const int x = q % TL_VK, b = (q / TL_VK) % TL_HJ, aa = q / (TL_VK * TL_HJ);
                 const int gp = p0 - 2 + aa, gj = j0 - 2 + b, gk = k0 - TL_VK0 + x;
                 const bool in = gp >= 0 && gp < a.np && gj >= 0 && gj < L && gk >= 0 && gk < L;
-                sm.vx[0][q] = in ? a.cvox[((int64_t)gp * L + gj) * L + gk] : (uint8_t)0;
+                sm.vx[q] = in ? a.cvox[((int64_t)gp * L + gj) * L + gk] : (uint8_t)0;
             }
             for (int q = tid; q < TL_HI * TL_HJ * TL_PK; q += TL_THREADS) {
                 const int x = q % TL_PK, b = (q / TL_PK) % TL_HJ, aa = q / (TL_PK * TL_HJ);
                 const int gp = p0 - 2 + aa, gj = j0 - 2 + b, gk = k0 - TL_PK0 + x;
                 const bool in = gp >= 0 && gp < a.np && gj >= 0 && gj < L && gk >= 0 && gk < L;
-                sm.po[0][q] = in ? a.pairop[((int64_t)gp * L + gj) * L + gk] : 0.0;
+                sm.po[q] = in ? a.pairop[((int64_t)gp * L + gj) * L + gk] : 0.0;
             }
         }
-        // ---- the tile's stamped sites (independent of the staged data: runs under the loads)
-        const bool all = (a.mode & TM_ALL) != 0;
-        if (!all) {
-            if (wid == 0) {
-                unsigned bits[2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int row = lane + 32 * h, p = p0 + (row >> 3), j = j0 + (row & 7);
-                    unsigned b = 0;
-                    if (p < a.p_hi && j < L && k0 < L) {
-                        const int s0 = (p * L + j) * L + k0;
-                        const unsigned w0 = a.stamp[s0 >> 5], w1 = a.stamp[(s0 >> 5) + 1];
-                        b = __funnelshift_r(w0, w1, s0 & 31);
-                        if (L - k0 < 32) b &= (1u << (L - k0)) - 1u;
-                    }
-                    bits[h] = b;
-                }
-                const int mine = __popc(bits[0]) + __popc(bits[1]);
-                int inc = mine;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int u = __shfl_up_sync(0xffffffffu, inc, d);
-                    if (lane >= d) inc += u;
-                }
-                int pos = inc - mine;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    unsigned b = bits[h];
-                    const int row = lane + 32 * h;
-                    while (b) {
-                        const int e = __ffs(b) - 1;
-                        b &= b - 1;
-                        sm.dlist[pos++] = (uint16_t)(row * TL_K + e);
-                    }
-                }
-                if (lane == 31) sm.n_dirty = (unsigned)inc;
-            }
-        }
-        if (TMA) mbar_wait(&sm.bar[buf], (unsigned)((it >> 1) & 1));
         __syncthreads();
-        const uint8_t *sv = sm.vx[buf];
-        const double *sp = sm.po[buf];
-
-        // ---- refresh: 32 sites per warp and trip
         const int n_eval = all ? TL_SITES : (int)sm.n_dirty;
-        for (int q0 = 32 * wid; q0 < n_eval; q0 += 32 * TL_WARPS) {
+        ++n_staged;
+        // ---- up to 32 sites per warp and trip; a short list is dealt to all warps (fewer sites per trip:
+        // the trips are latency chains, so four warps with 16 sites each finish sooner than two with 32)
+        int spt = 32;
+        if (n_eval < 32 * TL_WARPS) {
+            const int per = (n_eval + TL_WARPS - 1) / TL_WARPS;
+            spt = per <= 8 ? 8 : per <= 16 ? 16 : 32;
+        }
+        for (int q0 = spt * wid; q0 < n_eval; q0 += spt * TL_WARPS) {
             const int q = q0 + lane;
-            bool active = q < n_eval;
+            bool active = lane < spt && q < n_eval;
             const int e = active ? (all ? q : (int)sm.dlist[q]) : 0;
             const int li = e >> 8, lj = (e >> 5) & 7, lk = e & 31;
             const int p = p0 + li, j = j0 + lj, k = k0 + lk;
             if (all) active = active && p < a.p_hi && j < L && k < L;
-            tile_eval(a, sm, sm.w[wid], sv, sp, li, lj, lk, p, j, k, active);
+            if (EVAL == 0) tile_eval_packed(a, sm.tab, sm.dp, sm.w[wid], sm.vx, sm.po, li, lj, lk, p, j, k, active);
+            else tile_eval_serial(a, sm.tab, sm.vx, sm.po, li, lj, lk, p, j, k, active);
         }
-        if (!all && tid == 0) n_refreshed += (unsigned)n_eval;
-        if (!(a.mode & TM_STREAM)) {
-            __syncthreads();                                   // the buffer may be refilled two tiles on
-            continue;
-        }
-        __syncthreads();                                       // refreshed rate sums are visible to the CTA
-
-        // ---- stream: warp = (plane, band of 4 rows), lane = k; one Philox block per lane
-        {
-            const int li = wid >> 1, band = wid & 1;
-            const int p = p0 + li, k = k0 + lane;
-            const int jb0 = j0 + 4 * band;
-            const bool col = p < a.p_hi && k < L;
-            double R[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int j = jb0 + r;
-                R[r] = (col && j < L) ? __ldcg(a.site_rate + ((int64_t)p * L + j) * L + k) : 0.0;
-            }
-            if (p == a.top_plane && col) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int j = jb0 + r;
-                    if (j < L) {
-                        const double d = __ldcg(a.dep_rate + j * L + k);
-                        if (d == d) R[r] = d + R[r];
-                    }
-                }
-            }
-            double rsum = ((R[0] + R[1]) + R[2]) + R[3];
-            double rmax = fmax(fmax(R[0], R[1]), fmax(R[2], R[3]));
-            unsigned fmask = 0;
-            if (tau > 0.0 && rmax > 0.0) {
-                const u32x4 rnd = philox4x32_10(u32x4{(uint32_t)(jb0 >> 2) * (uint32_t)L + (uint32_t)k, (uint32_t)(a.i_off + p),
-                                                      a.sweep, (uint32_t)STREAM_FIRE_TILE},
-                                                (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-                const uint32_t words[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-                const double tau32 = tau * 4294967296.0;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const double d = (double)words[r];
-                    if (d <= R[r] * tau32) {              // else digit > floor(2^32 x) >= floor(2^32 p): cannot fire
-                        const uint64_t gsite = ((uint64_t)(a.i_off + p) * (uint64_t)L + (uint64_t)(jb0 + r)) * (uint64_t)L + (uint64_t)k;
-                        if (tile_fire_exact(R[r] * tau, d, a.seed, gsite, a.sweep)) fmask |= 1u << r;
-                    }
-                }
-            }
-            rsum = warp_sum(rsum);
-            rmax = warp_max(rmax);
-            if (lane == 0 && p < a.p_hi) {
-                const int64_t slot = ((int64_t)(p - a.p_lo) * tiles_per_iblock + (jb * a.nkb + kb)) * 2 + band;
-                a.blk_sum[slot] = rsum;
-                a.blk_max[slot] = rmax;
-            }
-            // fired sites: one list reservation per warp
-            const unsigned any = __ballot_sync(0xffffffffu, fmask != 0);
-            if (any) {
-                const int mine = __popc(fmask);
-                int inc = mine;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int u = __shfl_up_sync(0xffffffffu, inc, d);
-                    if (lane >= d) inc += u;
-                }
-                unsigned int base = 0;
-                if (lane == 31) base = atomicAdd(&a.ss->n_fired, (unsigned)inc);
-                base = __shfl_sync(0xffffffffu, base, 31);
-                unsigned int pos = base + (unsigned)(inc - mine);
-                while (fmask) {
-                    const int r = __ffs(fmask) - 1;
-                    fmask &= fmask - 1;
-                    if (pos < a.cap_fired) a.fired[pos] = (p * L + (jb0 + r)) * L + k;
-                    else a.ss->overflow = 1;
-                    ++pos;
-                }
-            }
-        }
-        __syncthreads();                                       // the buffer may be refilled two tiles on
+        if (!all && tid == 0) atomicAdd(&a.ss->n_dirty, (unsigned)n_eval);
+        __syncthreads();                                       // the tile (and the list) may be overwritten
     }
-    if (tid == 0 && n_refreshed) atomicAdd(&a.ss->n_dirty, n_refreshed);
 }
 
 // ---- resident tile state -----------------------------------------------------------------------
@@ -581,15 +525,32 @@ static int tile_maps_ensure(cet_ctx *c)
     return 0;
 }
 
-// Number of (plane, tile, row band) partial sums per plane written by the stream phase.
-int tile_parts_per_plane(const cet_ctx *c)
+template <bool TMA, int EVAL>
+static int tile_launch(cet_ctx *c, const TileArgs &a, int *blocks_per_sm)
 {
-    return (int)(((c->n1 + TL_J - 1) / TL_J) * ((c->n2 + TL_K - 1) / TL_K) * 2);
+    const size_t smem = sizeof(TileSmem<EVAL>) + 1024;
+    if (*blocks_per_sm == 0) {
+        CET_CUDA(cudaFuncSetAttribute(rates_tile3d_kernel<TMA, EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rates_tile3d_kernel<TMA, EVAL>, TL_THREADS, smem));
+        CET_REQUIRE(nb >= 1, "rates_tile3d_kernel does not fit an SM");
+        *blocks_per_sm = nb;
+    }
+    const int grid = std::min(a.n_tiles, sm_count(c) * *blocks_per_sm);
+    if (TMA) {
+        rates_tile3d_kernel<TMA, EVAL><<<grid, TL_THREADS, smem, c->stream>>>(a, *(const CUtensorMap *)c->tmap_vox,
+                                                                              *(const CUtensorMap *)c->tmap_po);
+    } else {
+        CUtensorMap dummy;
+        memset(&dummy, 0, sizeof(dummy));
+        rates_tile3d_kernel<TMA, EVAL><<<grid, TL_THREADS, smem, c->stream>>>(a, dummy, dummy);
+    }
+    CET_CUDA(cudaGetLastError());
+    return 0;
 }
 
-// One pass of the fused kernel over local planes [p_lo, p_hi).  mode: TM_ALL re-evaluates every site
-// (else the stamped ones), TM_STREAM adds the fire test and the partial sums.
-int tile_pass(cet_ctx *c, int p_lo, int p_hi, int mode, uint64_t seed, uint32_t sweep)
+// One pass of the tile kernel over local planes [p_lo, p_hi): every site (all) or the stamped ones.
+int tile_pass(cet_ctx *c, int p_lo, int p_hi, bool all)
 {
     if (p_hi <= p_lo) return 0;
     if (int rc = rate_tables_ensure(c)) return rc;
@@ -597,8 +558,7 @@ int tile_pass(cet_ctx *c, int p_lo, int p_hi, int mode, uint64_t seed, uint32_t 
     memset(&a, 0, sizeof(a));
     a.cvox = c->cvox; a.pairop = c->pairop; a.T = c->T;
     a.site_rate = c->site_rate; a.dep_rate = c->dep_rate; a.stamp = c->stamp;
-    a.ss = c->sweep; a.fired = c->fired; a.cap_fired = (unsigned int)c->cap_fired;
-    a.blk_sum = c->blk_sum; a.blk_max = c->blk_max; a.tab = c->rate_tab;
+    a.ss = c->sweep; a.tab = c->rate_tab;
     a.P = c->rp;
     a.L = (int)c->n1; a.n0 = (int)c->n0; a.np = (int)c->np; a.i_off = (int)(c->i_begin - c->halo);
     a.p_lo = p_lo; a.p_hi = p_hi;
@@ -606,25 +566,13 @@ int tile_pass(cet_ctx *c, int p_lo, int p_hi, int mode, uint64_t seed, uint32_t 
     a.top_plane = (top >= p_lo && top < p_hi) ? top : -1;
     a.njb = (int)((c->n1 + TL_J - 1) / TL_J); a.nkb = (int)((c->n2 + TL_K - 1) / TL_K);
     a.n_tiles = ((p_hi - p_lo + TL_I - 1) / TL_I) * a.njb * a.nkb;
-    a.mode = mode; a.seed = seed; a.sweep = sweep;
-    const int grid = std::min(a.n_tiles, sm_count(c));
+    a.mode = all ? TM_ALL : 0;
     const bool tma = tile_tma_usable(c);
-    if (!c->tile_attr_set) {
-        CET_CUDA(cudaFuncSetAttribute(sweep_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem) + 1024));
-        CET_CUDA(cudaFuncSetAttribute(sweep_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem) + 1024));
-        c->tile_attr_set = true;
-    }
-    if (tma) {
-        if (int rc = tile_maps_ensure(c)) return rc;
-        sweep_tile_kernel<true><<<grid, TL_THREADS, sizeof(TileSmem) + 1024, c->stream>>>(a, *(const CUtensorMap *)c->tmap_vox,
-                                                                                  *(const CUtensorMap *)c->tmap_po);
-    } else {
-        CUtensorMap dummy;
-        memset(&dummy, 0, sizeof(dummy));
-        sweep_tile_kernel<false><<<grid, TL_THREADS, sizeof(TileSmem) + 1024, c->stream>>>(a, dummy, dummy);
-    }
-    CET_CUDA(cudaGetLastError());
-    return 0;
+    const bool serial = (c->debug_flags & 4) != 0;
+    if (tma) if (int rc = tile_maps_ensure(c)) return rc;
+    int *bps = &c->tile_blocks[(tma ? 2 : 0) + (serial ? 1 : 0)];
+    if (tma) return serial ? tile_launch<true, 1>(c, a, bps) : tile_launch<true, 0>(c, a, bps);
+    return serial ? tile_launch<false, 1>(c, a, bps) : tile_launch<false, 0>(c, a, bps);
 }
 
 }  // namespace cet

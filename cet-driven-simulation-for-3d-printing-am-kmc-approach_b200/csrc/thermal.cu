@@ -301,7 +301,7 @@ int cet_thermal_cet(cet_ctx *c, const cet_thermal_params *p)
 {
     CET_REQUIRE(c && p, "cet_thermal_cet: NULL argument");
     cet::DeviceGuard dg(c->device);
-    c->tile_valid = false; c->stamps_pending = false;
+    c->tile_valid = false;
     return thermal_cet_step(c, p, nullptr);
 }
 
@@ -320,7 +320,7 @@ int cet_thermal_full(cet_ctx *c, const cet_thermal_full_params *p, const double 
     a.dt = p->dt; a.alpha = p->alpha; a.rho_cp = p->rho_cp; a.latent_over_cp = p->latent_over_cp;
     a.inv_dt_latent = 1.0 / (p->dt > 1e-12 ? p->dt : 1e-12);   // mask / max(dt, 1e-12), thermal_solver.py:98
     int rc = launch_thermal<true>(c, a);
-    c->tile_valid = false; c->stamps_pending = false;
+    c->tile_valid = false;
     if (rc) return rc;
     CET_CUDA(cudaStreamSynchronize(c->stream));   // q_top host pointer is borrowed for the call only
     return 0;

@@ -22,16 +22,16 @@
 
 namespace cet {
 
-constexpr int TL_I = 8, TL_J = 8, TL_K = 32;             // sites of one tile (planes x rows x k)
+constexpr int TL_I = 4, TL_J = 8, TL_K = 32;             // sites of one tile (planes x rows x k)
 constexpr int TL_SITES = TL_I * TL_J * TL_K;
 constexpr int TL_HI = TL_I + 4, TL_HJ = TL_J + 4;        // staged planes / rows (halo 2)
 constexpr int TL_VK = 64, TL_VK0 = 16;                   // staged cvox bytes per row and offset of the tile's first k: a u8 box row of 48 B
                                                          // faults (illegal instruction) on B200 although it is a multiple of 16 B; 64 B works
                                                          // (scripts/tma_probe.cu)
 constexpr int TL_PK = TL_K + 4, TL_PK0 = 2;              // staged pairop doubles per row
-constexpr int TL_VBYTES = TL_HI * TL_HJ * TL_VK;         // 9 216
-constexpr int TL_PBYTES = TL_HI * TL_HJ * TL_PK * 8;     // 41 472
-constexpr int TL_THREADS = 512, TL_WARPS = TL_THREADS / 32;
+constexpr int TL_VBYTES = TL_HI * TL_HJ * TL_VK;         // 6 144
+constexpr int TL_PBYTES = TL_HI * TL_HJ * TL_PK * 8;     // 27 648
+constexpr int TL_THREADS = 128, TL_WARPS = TL_THREADS / 32;
 
 enum { TC_OUTSIDE = 0, TC_OTHER = 1, TC_DEFECT = 3, TC_EMPTY = 8, TC_W = 9, TC_RE = 11, TC_C = 13 };
 

@@ -165,8 +165,7 @@ int cet_kmc_run(cet_ctx *ctx, int64_t step0, int64_t n_steps, double defect_frac
 
 /* ---- synchronous-sublattice sweeps (large lattices) ----
  * A context whose clock is fresh (tau == 0) first runs one priming pass that only measures the total
- * rate, so that every counted sweep is a real one.  The rate sums of the sites the last sweep changed
- * are brought up to date by the next sweep (or by cet_rates_download). */
+ * rate, so that every counted sweep is a real one. */
 int cet_sweep_run(cet_ctx *ctx, int64_t n_sweeps, const cet_sweep_params *sp,
                   const cet_thermal_params *tp, cet_sweep_result *res);
 int cet_sweep_reset(cet_ctx *ctx); /* zero the sweep counter, clock, tau and event counters */
@@ -208,17 +207,17 @@ int cet_grains_download_labels(cet_ctx *ctx, int32_t *labels);
 /* Test hook: number of sites whose cached neighbour-state word differs from a fresh gather
  * (-1 when the cache is declared stale). */
 int cet_debug_nst_mismatches(cet_ctx *ctx, int64_t *n_bad);
-/* Test / profiling hook: kernel selection of cet_sweep_run.  bit 0: stage the tiles of the fused
- * sweep kernel with cooperative loads instead of TMA; bit 1: run the gather kernels of the first
- * design (stream, stamp scan, list-driven re-evaluation) instead of the fused tile kernel. */
+/* Test / profiling hook: which kernels keep the rate sums current in cet_sweep_run.  bit 0: stage the
+ * tiles of the tile kernel with cooperative loads instead of TMA; bit 1: the gather refresh of the
+ * first design (stamp scan + list-driven re-evaluation) instead of the tile kernel; bit 2: the tile
+ * kernel walks the 14 neighbour slots per lane instead of compacting the pairs across the warp;
+ * bit 3: dense rebuilds by the gather kernel of rates.cu even when the tile kernel refreshes. */
 int cet_debug_flags(cet_ctx *ctx, int flags);
 
 /* ---- per-kernel device timing: CUDA event pairs recorded on the context stream around every
  * launch of a kind while enabled.  kind: 0 sweep stream (fire decision), 1 sweep apply,
  * 2 thermal stencil, 3 dense rate kernel, 4 halo exchange, 5 whole sweep, 6 sweep pick,
- * 7 neighbour-rate refresh, 8 totals all-reduce, 9 ghost-zone cache + rate rebuild after the exchange.
- * With the fused tile kernel, kind 0 is the pass that refreshes the stamped sites and streams, and
- * kind 3 the pass that re-evaluates every site (after a thermal step) and streams. */
+ * 7 neighbour-rate refresh, 8 totals all-reduce, 9 ghost-zone cache + rate rebuild after the exchange. */
 int cet_profile_enable(cet_ctx *ctx, int on);
 int cet_profile_read(cet_ctx *ctx, int kind, double *ms_total, int64_t *launches, int reset);
 

@@ -1,7 +1,7 @@
 """GPU: synchronous-sublattice sweeps (csrc/sweep.cu, csrc/sweep_tile.cu) — invariants, determinism
 and level-3 parity (trajectory observables against the serial oracle within statistical bounds).
-FUSED = the TMA-staged tile kernel, NO_TMA = the same kernel with cooperative tile loads,
-GATHER = the kernels of the first design (Context.debug_flags)."""
+Refresh variants (Context.debug_flags): TILE = the TMA-staged tile kernel, NO_TMA = the same kernel with
+cooperative tile loads, SERIAL = its per-lane pair loop, GATHER = the list-driven gather refresh."""
 import numpy as np
 import pytest
 
@@ -15,7 +15,8 @@ def _sweep_params(cet, seed, L, eps=0.02, p_max=0.25, defect_fraction=0.0, therm
     return sp
 
 
-FUSED, NO_TMA, GATHER = 0, 1, 2
+TILE, NO_TMA, GATHER, SERIAL = 0, 1, 2, 4
+FUSED = TILE
 
 
 def _setup(cet, L, seed=3, c=0.1, flags=FUSED):
@@ -79,24 +80,28 @@ def test_first_sweep_is_primed(cet, oracle, flags):
     ctx.close()
 
 
-@pytest.mark.parametrize("L", [64, 80])
-def test_tma_and_cooperative_tile_loads_agree(cet, L):
-    """The fused kernel with TMA-staged tiles and with cooperative loads runs the same trajectory bit
-    for bit (same Philox keys, same arithmetic): lattice, counters and resident rates."""
+@pytest.mark.parametrize("L", [64, 80, 50])
+def test_refresh_variants_agree(cet, L):
+    """Every refresh variant — TMA tile kernel, cooperative tile loads, per-lane pair loop, and the
+    gather kernels of the first design — runs the same trajectory bit for bit (the stream / pick /
+    apply kernels are shared and every variant's rates equal the per-event code): lattice, counters
+    and resident rates."""
     from cetkmc._config import thermal_params
     outs = []
-    for flags in (FUSED, NO_TMA):
+    for flags in (TILE, NO_TMA, SERIAL, SERIAL | NO_TMA, GATHER, TILE | 8):
         ctx, st, th, ph, T, df = _setup(cet, L, flags=flags)
         res = ctx.sweep_run(7, _sweep_params(cet, 5, L, eps=0.01, p_max=0.2, defect_fraction=0.01, thermal_every=3),
                             thermal_params(1e-6, nan_to_num=True))
         outs.append((res, ctx.download(state=True, theta=True, phi=True, T=True), ctx.rates_download()))
         ctx.close()
-    (r1, f1, (s1, d1)), (r2, f2, (s2, d2)) = outs
-    assert r1 == r2 and r1["events_applied"] > 100
-    for k in f1:
-        np.testing.assert_array_equal(f1[k], f2[k])
-    np.testing.assert_array_equal(s1, s2)
-    np.testing.assert_array_equal(d1, d2)
+    r1, f1, (s1, d1) = outs[0]
+    assert r1["events_applied"] > 100
+    for n, (r2, f2, (s2, d2)) in enumerate(outs[1:], 1):
+        assert r1 == r2, f"variant #{n}"
+        for k in f1:
+            np.testing.assert_array_equal(f1[k], f2[k], err_msg=f"variant #{n} {k}")
+        np.testing.assert_array_equal(s1, s2, err_msg=f"variant #{n}")
+        np.testing.assert_array_equal(d1, d2, err_msg=f"variant #{n}")
 
 
 def test_oriented_empty_sites_take_the_gather_path(cet):
@@ -188,7 +193,7 @@ def test_level3_observables_vs_serial_oracle(cet, oracle):
     assert np.all(np.abs(mo - mg) <= tol), (mo, mg, tol)
 
 
-@pytest.mark.parametrize("L,flags", [(36, FUSED), (64, FUSED), (96, FUSED), (36, GATHER)])
+@pytest.mark.parametrize("L,flags", [(36, TILE), (64, TILE), (96, TILE), (96, SERIAL), (36, GATHER)])
 def test_resident_rates_equal_rebuild_after_sweeps(cet, L, flags):
     """Neighbour-rate refresh invariant: after N sweeps (thermal steps and defect injection
     included) the resident rate sums equal a dense rebuild by the gather kernel of rates.cu bit for
@@ -199,7 +204,7 @@ def test_resident_rates_equal_rebuild_after_sweeps(cet, L, flags):
     res = ctx.sweep_run(9, _sweep_params(cet, 21, L, eps=0.01, p_max=0.2, defect_fraction=0.02, thermal_every=4),
                         thermal_params(1e-6, nan_to_num=True))
     assert res["events_applied"] > 100 and res["sites_refreshed"] > res["events_applied"]
-    sr1, dr1 = ctx.rates_download()          # resident arrays as the sweeps left them (pending refreshes flushed)
+    sr1, dr1 = ctx.rates_download()          # resident arrays as the sweeps left them
     if flags == GATHER:
         assert ctx.nst_mismatches() == 0
     ctx.rates_build()                        # dense rebuild from the lattice
