@@ -105,8 +105,9 @@ struct TileSite {
 };
 
 // Per-site half: class codes of the 14 neighbours from the staged tile, temperatures, tile_site_prep.
+// Tpre != nullptr: T[s-1], T[s], T[s+1] were loaded before the tile arrived (the trip's only global reads).
 __device__ __forceinline__ TileSite tile_site(const TileArgs &a, const double *tab, const uint8_t *sv, const double *sp, int li,
-                                              int lj, int lk, int p, int j, int k, bool active)
+                                              int lj, int lk, int p, int j, int k, bool active, const double *Tpre)
 {
     TileSite r;
     const int vidx = ((li + 2) * TL_HJ + (lj + 2)) * TL_VK + lk + TL_VK0;
@@ -128,11 +129,11 @@ __device__ __forceinline__ TileSite tile_site(const TileArgs &a, const double *t
             T_self = sp[r.pidx];                                     // an empty site's pairop is its temperature
             T_m = T_self; T_p = T_self;
             if ((wlo | whi) & 0x11111111u) {                         // an occupied neighbour: grad_z is needed (:151-153)
-                if (k > 0) T_m = (sv[vidx - 1] & 15u) == TC_EMPTY ? sp[r.pidx - 1] : a.T[r.s - 1];
-                if (k < a.L - 1) T_p = (sv[vidx + 1] & 15u) == TC_EMPTY ? sp[r.pidx + 1] : a.T[r.s + 1];
+                if (k > 0) T_m = (sv[vidx - 1] & 15u) == TC_EMPTY ? sp[r.pidx - 1] : (Tpre ? Tpre[0] : a.T[r.s - 1]);
+                if (k < a.L - 1) T_p = (sv[vidx + 1] & 15u) == TC_EMPTY ? sp[r.pidx + 1] : (Tpre ? Tpre[2] : a.T[r.s + 1]);
             }
         } else if ((code & 1u) && code != TC_DEFECT) {
-            T_self = a.T[r.s];
+            T_self = Tpre ? Tpre[1] : a.T[r.s];
         }
     }
     const uint64_t w = (uint64_t)wlo | ((uint64_t)whi << 32);
@@ -153,11 +154,11 @@ __device__ __forceinline__ void tile_store(const TileArgs &a, const TileSite &t,
 // EVAL 0 — 32 sites per warp, their pairs compacted across the warp (all 32 lanes call).
 __device__ __forceinline__ void tile_eval_packed(const TileArgs &a, const double *tab, const int *dp, TileWarpSmem &ws,
                                                  const uint8_t *sv, const double *sp, int li, int lj, int lk, int p, int j,
-                                                 int k, bool active)
+                                                 int k, bool active, const double *Tpre)
 {
     const cet_rate_params &P = a.P;
     const int lane = threadIdx.x & 31;
-    const TileSite t = tile_site(a, tab, sv, sp, li, lj, lk, p, j, k, active);
+    const TileSite t = tile_site(a, tab, sv, sp, li, lj, lk, p, j, k, active, Tpre);
     const uint64_t pm = t.q.pm;
     const bool is_emp = t.q.is_emp;
     if (pm) { ws.A[lane] = t.q.A; ws.B[lane] = t.q.B; }
@@ -218,10 +219,10 @@ __device__ __forceinline__ void tile_eval_packed(const TileArgs &a, const double
 
 // EVAL 1 — every lane walks the 14 slots of its own site; neighbour offsets are immediates.
 __device__ __forceinline__ void tile_eval_serial(const TileArgs &a, const double *tab, const uint8_t *sv, const double *sp, int li,
-                                                 int lj, int lk, int p, int j, int k, bool active)
+                                                 int lj, int lk, int p, int j, int k, bool active, const double *Tpre)
 {
     const cet_rate_params &P = a.P;
-    const TileSite t = tile_site(a, tab, sv, sp, li, lj, lk, p, j, k, active);
+    const TileSite t = tile_site(a, tab, sv, sp, li, lj, lk, p, j, k, active, Tpre);
     double sum = t.q.sum0;
     if (__any_sync(0xffffffffu, t.q.pm != 0)) {
         const bool is_emp = t.q.is_emp;
@@ -239,7 +240,7 @@ __device__ __forceinline__ void tile_eval_serial(const TileArgs &a, const double
     if (active) tile_store(a, t, sum, p, j, k);
 }
 
-template <bool TMA, int EVAL>
+template <int STAGE, int EVAL>
 __global__ void __launch_bounds__(TL_THREADS, EVAL == 0 ? 4 : 5)
     rates_tile3d_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ CUtensorMap tm_vox,
                         const __grid_constant__ CUtensorMap tm_po)
@@ -251,6 +252,7 @@ __global__ void __launch_bounds__(TL_THREADS, EVAL == 0 ? 4 : 5)
 
     for (int q = tid; q < RT_TABLE_DOUBLES; q += TL_THREADS) sm.tab[q] = a.tab[q];
     if (tid < 14) sm.dp[tid] = ((int)c_nb_off[tid][0] * TL_HJ + c_nb_off[tid][1]) * TL_PK + c_nb_off[tid][2];
+    constexpr bool TMA = STAGE == 0;
     if (TMA && tid == 0) {
         mbar_init(&sm.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -259,7 +261,28 @@ __global__ void __launch_bounds__(TL_THREADS, EVAL == 0 ? 4 : 5)
 
     const int tiles_per_iblock = a.njb * a.nkb;
     const bool all = (a.mode & TM_ALL) != 0;
+    constexpr int NH = (TL_I * TL_J + 31) / 32;
+    // stamp words of a tile's rows (warp 0, one row per lane and h): loaded one tile ahead
+    auto load_stamps = [&](int t, unsigned *bits) {
+        const int kb = t % a.nkb, jb = (t / a.nkb) % a.njb, ib = t / tiles_per_iblock;
+        const int p0 = a.p_lo + TL_I * ib, j0 = TL_J * jb, k0 = TL_K * kb;
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            const int row = lane + 32 * h, p = p0 + (row >> 3), j = j0 + (row & 7);
+            unsigned b = 0;
+            if (t < a.n_tiles && row < TL_I * TL_J && p < a.p_hi && j < L && k0 < L) {
+                const int s0 = (p * L + j) * L + k0;
+                const unsigned w0 = a.stamp[s0 >> 5], w1 = a.stamp[(s0 >> 5) + 1];
+                b = __funnelshift_r(w0, w1, s0 & 31);
+                if (L - k0 < 32) b &= (1u << (L - k0)) - 1u;
+            }
+            bits[h] = b;
+        }
+    };
+    unsigned next_bits[NH];
+    if (!all && wid == 0) load_stamps((int)blockIdx.x, next_bits);
     unsigned int n_staged = 0;                  // tiles staged so far: the mbarrier's phase parity
+    unsigned int n_refreshed = 0;
     for (int t = (int)blockIdx.x; t < a.n_tiles; t += (int)gridDim.x) {
         const int kb = t % a.nkb, jb = (t / a.nkb) % a.njb, ib = t / tiles_per_iblock;
         const int p0 = a.p_lo + TL_I * ib, j0 = TL_J * jb, k0 = TL_K * kb;
@@ -269,46 +292,85 @@ __global__ void __launch_bounds__(TL_THREADS, EVAL == 0 ? 4 : 5)
             tma_load_3d(sm.po, &tm_po, &sm.bar, k0 - TL_PK0, j0 - 2, p0 - 2);
         }
         // ---- the tile's stamped sites, listed by warp 0 while the loads are in flight
-        if (!all && wid == 0) {
-            constexpr int NH = (TL_I * TL_J + 31) / 32;
-            unsigned bits[NH];
-            int mine = 0;
+        int spt = 32, e0 = 0;
+        bool act0 = false;
+        double Tpre[3] = {1.0, 1.0, 1.0};
+        if (!all) {
+            if (wid == 0) {
+                unsigned bits[NH];
+                int mine = 0;
 #pragma unroll
-            for (int h = 0; h < NH; ++h) {
-                const int row = lane + 32 * h, p = p0 + (row >> 3), j = j0 + (row & 7);
-                unsigned b = 0;
-                if (row < TL_I * TL_J && p < a.p_hi && j < L && k0 < L) {
-                    const int s0 = (p * L + j) * L + k0;
-                    const unsigned w0 = a.stamp[s0 >> 5], w1 = a.stamp[(s0 >> 5) + 1];
-                    b = __funnelshift_r(w0, w1, s0 & 31);
-                    if (L - k0 < 32) b &= (1u << (L - k0)) - 1u;
+                for (int h = 0; h < NH; ++h) { bits[h] = next_bits[h]; mine += __popc(bits[h]); }
+                load_stamps(t + (int)gridDim.x, next_bits);           // the next tile's, used one iteration on
+                int inc = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += u;
                 }
-                bits[h] = b;
-                mine += __popc(b);
-            }
-            int inc = mine;
+                int pos = inc - mine;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int u = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += u;
-            }
-            int pos = inc - mine;
-#pragma unroll
-            for (int h = 0; h < NH; ++h) {
-                unsigned b = bits[h];
-                const int row = lane + 32 * h;
-                while (b) {
-                    const int e = __ffs(b) - 1;
-                    b &= b - 1;
-                    sm.dlist[pos++] = (uint16_t)(row * TL_K + e);
+                for (int h = 0; h < NH; ++h) {
+                    unsigned b = bits[h];
+                    const int row = lane + 32 * h;
+                    while (b) {
+                        const int e = __ffs(b) - 1;
+                        b &= b - 1;
+                        sm.dlist[pos++] = (uint16_t)(row * TL_K + e);
+                    }
                 }
+                if (lane == 31) sm.n_dirty = (unsigned)inc;
             }
-            if (lane == 31) sm.n_dirty = (unsigned)inc;
+            __syncthreads();
+            // a short list is dealt to all warps (fewer sites per trip: the trips are latency chains), and the
+            // temperatures of the first trip are requested before the tile arrives
+            const int n_d = (int)sm.n_dirty;
+            if (n_d < 32 * TL_WARPS) {
+                const int per = (n_d + TL_WARPS - 1) / TL_WARPS;
+                spt = per <= 8 ? 8 : per <= 16 ? 16 : 32;
+            }
+            const int q = spt * wid + lane;
+            act0 = lane < spt && q < n_d;
+            if (act0) {
+                e0 = (int)sm.dlist[q];
+                const int p = p0 + (e0 >> 8), j = j0 + ((e0 >> 5) & 7), k = k0 + (e0 & 31);
+                const int s = (p * L + j) * L + k;
+                Tpre[1] = a.T[s];
+                Tpre[0] = k > 0 ? a.T[s - 1] : Tpre[1];
+                Tpre[2] = k < L - 1 ? a.T[s + 1] : Tpre[1];
+            }
         }
         if (TMA) {
             mbar_wait(&sm.bar, n_staged & 1u);
+        } else if (STAGE == 1) {
+            // vector loads (L % 16 == 0): a warp copies whole rows of the tile, 16 bytes per lane; rows and
+            // 16-byte chunks outside the lattice become zeros (class code 0 = outside)
+            constexpr int ROWS = TL_HI * TL_HJ, PCH = TL_PK / 2, VCH = TL_VK / 16, VR = 32 / VCH;
+#pragma unroll 4
+            for (int row = wid; row < ROWS; row += TL_WARPS) {
+                const int aa = row / TL_HJ, b = row - aa * TL_HJ;
+                const int gp = p0 - 2 + aa, gj = j0 - 2 + b, gk = k0 - TL_PK0 + 2 * lane;
+                if (lane < PCH) {
+                    double2 val = make_double2(0.0, 0.0);
+                    if (gp >= 0 && gp < a.np && gj >= 0 && gj < L && gk >= 0 && gk + 1 < L)
+                        val = __ldg(reinterpret_cast<const double2 *>(a.pairop + ((int64_t)gp * L + gj) * L + gk));
+                    *reinterpret_cast<double2 *>(sm.po + row * TL_PK + 2 * lane) = val;
+                }
+            }
+#pragma unroll 2
+            for (int r0 = wid * VR; r0 < ROWS; r0 += TL_WARPS * VR) {
+                const int row = r0 + lane / VCH, ch = lane % VCH;
+                const int aa = row / TL_HJ, b = row - aa * TL_HJ;
+                const int gp = p0 - 2 + aa, gj = j0 - 2 + b, gk = k0 - TL_VK0 + 16 * ch;
+                if (row < ROWS) {
+                    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+                    if (gp >= 0 && gp < a.np && gj >= 0 && gj < L && gk >= 0 && gk + 15 < L)
+                        val = __ldg(reinterpret_cast<const uint4 *>(a.cvox + ((int64_t)gp * L + gj) * L + gk));
+                    *reinterpret_cast<uint4 *>(sm.vx + row * TL_VK + 16 * ch) = val;
+                }
+            }
         } else {
-            // cooperative loads (lattices whose row stride TMA cannot describe): zero outside the local array
+            // scalar loads (any L): zero outside the local array
             for (int q = tid; q < TL_VBYTES; q += TL_THREADS) {
                 const int x = q % TL_VK, b = (q / TL_VK) % TL_HJ, aa = q / (TL_VK * TL_HJ);
                 const int gp = p0 - 2 + aa, gj = j0 - 2 + b, gk = k0 - TL_VK0 + x;
@@ -325,26 +387,24 @@ __global__ void __launch_bounds__(TL_THREADS, EVAL == 0 ? 4 : 5)
         __syncthreads();
         const int n_eval = all ? TL_SITES : (int)sm.n_dirty;
         ++n_staged;
-        // ---- up to 32 sites per warp and trip; a short list is dealt to all warps (fewer sites per trip:
-        // the trips are latency chains, so four warps with 16 sites each finish sooner than two with 32)
-        int spt = 32;
-        if (n_eval < 32 * TL_WARPS) {
-            const int per = (n_eval + TL_WARPS - 1) / TL_WARPS;
-            spt = per <= 8 ? 8 : per <= 16 ? 16 : 32;
-        }
+        // ---- up to 32 sites per warp and trip
+        bool first = !all;
         for (int q0 = spt * wid; q0 < n_eval; q0 += spt * TL_WARPS) {
             const int q = q0 + lane;
             bool active = lane < spt && q < n_eval;
-            const int e = active ? (all ? q : (int)sm.dlist[q]) : 0;
+            const int e = active ? (all ? q : (first ? e0 : (int)sm.dlist[q])) : 0;
             const int li = e >> 8, lj = (e >> 5) & 7, lk = e & 31;
             const int p = p0 + li, j = j0 + lj, k = k0 + lk;
             if (all) active = active && p < a.p_hi && j < L && k < L;
-            if (EVAL == 0) tile_eval_packed(a, sm.tab, sm.dp, sm.w[wid], sm.vx, sm.po, li, lj, lk, p, j, k, active);
-            else tile_eval_serial(a, sm.tab, sm.vx, sm.po, li, lj, lk, p, j, k, active);
+            const double *tp = first ? Tpre : nullptr;
+            if (EVAL == 0) tile_eval_packed(a, sm.tab, sm.dp, sm.w[wid], sm.vx, sm.po, li, lj, lk, p, j, k, active, tp);
+            else tile_eval_serial(a, sm.tab, sm.vx, sm.po, li, lj, lk, p, j, k, active, tp);
+            first = false;
         }
-        if (!all && tid == 0) atomicAdd(&a.ss->n_dirty, (unsigned)n_eval);
+        if (!all) n_refreshed += (unsigned)n_eval;
         __syncthreads();                                       // the tile (and the list) may be overwritten
     }
+    if (tid == 0 && n_refreshed) atomicAdd(&a.ss->n_dirty, n_refreshed);
 }
 
 // ---- resident tile state -----------------------------------------------------------------------
@@ -495,7 +555,6 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-static bool tile_tma_usable(const cet_ctx *c) { return c->n1 % 16 == 0 && c->n1 >= 64 && !(c->debug_flags & 1); }
 
 // Tensor maps over the local arrays (k fastest, then j, then plane); rebuilt when a pointer changed.
 static int tile_maps_ensure(cet_ctx *c)
@@ -525,25 +584,25 @@ static int tile_maps_ensure(cet_ctx *c)
     return 0;
 }
 
-template <bool TMA, int EVAL>
+template <int STAGE, int EVAL>
 static int tile_launch(cet_ctx *c, const TileArgs &a, int *blocks_per_sm)
 {
     const size_t smem = sizeof(TileSmem<EVAL>) + 1024;
     if (*blocks_per_sm == 0) {
-        CET_CUDA(cudaFuncSetAttribute(rates_tile3d_kernel<TMA, EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CET_CUDA(cudaFuncSetAttribute(rates_tile3d_kernel<STAGE, EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        CET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rates_tile3d_kernel<TMA, EVAL>, TL_THREADS, smem));
+        CET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rates_tile3d_kernel<STAGE, EVAL>, TL_THREADS, smem));
         CET_REQUIRE(nb >= 1, "rates_tile3d_kernel does not fit an SM");
         *blocks_per_sm = nb;
     }
     const int grid = std::min(a.n_tiles, sm_count(c) * *blocks_per_sm);
-    if (TMA) {
-        rates_tile3d_kernel<TMA, EVAL><<<grid, TL_THREADS, smem, c->stream>>>(a, *(const CUtensorMap *)c->tmap_vox,
+    if (STAGE == 0) {
+        rates_tile3d_kernel<STAGE, EVAL><<<grid, TL_THREADS, smem, c->stream>>>(a, *(const CUtensorMap *)c->tmap_vox,
                                                                               *(const CUtensorMap *)c->tmap_po);
     } else {
         CUtensorMap dummy;
         memset(&dummy, 0, sizeof(dummy));
-        rates_tile3d_kernel<TMA, EVAL><<<grid, TL_THREADS, smem, c->stream>>>(a, dummy, dummy);
+        rates_tile3d_kernel<STAGE, EVAL><<<grid, TL_THREADS, smem, c->stream>>>(a, dummy, dummy);
     }
     CET_CUDA(cudaGetLastError());
     return 0;
@@ -567,12 +626,21 @@ int tile_pass(cet_ctx *c, int p_lo, int p_hi, bool all)
     a.njb = (int)((c->n1 + TL_J - 1) / TL_J); a.nkb = (int)((c->n2 + TL_K - 1) / TL_K);
     a.n_tiles = ((p_hi - p_lo + TL_I - 1) / TL_I) * a.njb * a.nkb;
     a.mode = all ? TM_ALL : 0;
-    const bool tma = tile_tma_usable(c);
+    // staging: 16-byte vector loads when the rows allow it, scalar loads otherwise; TMA boxes on request
+    // (debug flag 16; measured slower for these short-row boxes, profiles/)
+    const bool aligned = c->n1 % 16 == 0 && c->n1 >= 64;
+    const int stage = (aligned && (c->debug_flags & 16)) ? 0 : (aligned && !(c->debug_flags & 1)) ? 1 : 2;
     const bool serial = (c->debug_flags & 4) != 0;
-    if (tma) if (int rc = tile_maps_ensure(c)) return rc;
-    int *bps = &c->tile_blocks[(tma ? 2 : 0) + (serial ? 1 : 0)];
-    if (tma) return serial ? tile_launch<true, 1>(c, a, bps) : tile_launch<true, 0>(c, a, bps);
-    return serial ? tile_launch<false, 1>(c, a, bps) : tile_launch<false, 0>(c, a, bps);
+    if (stage == 0) if (int rc = tile_maps_ensure(c)) return rc;
+    int *bps = &c->tile_blocks[stage * 2 + (serial ? 1 : 0)];
+    switch (stage * 2 + (serial ? 1 : 0)) {
+        case 0: return tile_launch<0, 0>(c, a, bps);
+        case 1: return tile_launch<0, 1>(c, a, bps);
+        case 2: return tile_launch<1, 0>(c, a, bps);
+        case 3: return tile_launch<1, 1>(c, a, bps);
+        case 4: return tile_launch<2, 0>(c, a, bps);
+        default: return tile_launch<2, 1>(c, a, bps);
+    }
 }
 
 }  // namespace cet

@@ -15,8 +15,8 @@ def _sweep_params(cet, seed, L, eps=0.02, p_max=0.25, defect_fraction=0.0, therm
     return sp
 
 
-TILE, NO_TMA, GATHER, SERIAL = 0, 1, 2, 4
-FUSED = TILE
+TILE, SCALAR, GATHER, SERIAL, TMA = 0, 1, 2, 4, 16
+FUSED, NO_TMA = TILE, SCALAR
 
 
 def _setup(cet, L, seed=3, c=0.1, flags=FUSED):
@@ -88,7 +88,7 @@ def test_refresh_variants_agree(cet, L):
     and resident rates."""
     from cetkmc._config import thermal_params
     outs = []
-    for flags in (TILE, NO_TMA, SERIAL, SERIAL | NO_TMA, GATHER, TILE | 8):
+    for flags in (TILE, SCALAR, TMA, SERIAL, SERIAL | TMA, GATHER, TILE | 8):
         ctx, st, th, ph, T, df = _setup(cet, L, flags=flags)
         res = ctx.sweep_run(7, _sweep_params(cet, 5, L, eps=0.01, p_max=0.2, defect_fraction=0.01, thermal_every=3),
                             thermal_params(1e-6, nan_to_num=True))
