@@ -16,6 +16,7 @@
 // Dense kernel shape: one CTA per 256 consecutive sites — see rate_tile.cuh.
 #include "ctx.cuh"
 #include "rate_tile.cuh"
+#include "tile_state.cuh"
 #include <algorithm>
 #include "reduce.cuh"
 
@@ -181,6 +182,233 @@ __global__ void __launch_bounds__(RT_THREADS, 5) dirty_eval_kernel(const __grid_
     RateSmem &sm = *reinterpret_cast<RateSmem *>(rate_dyn_smem);
     rate_smem_init(sm, a);
     rate_cta_loop<true>(a, sm, 0, (int)*n_list, list, queue);
+}
+
+// ---- refresh on the compact tile state (tile_state.cuh) -------------------------------------------
+// Same list, same queue-driven persistent CTAs, but a stamped site is re-evaluated from cvox (1 byte
+// class code per site) and pairop (one 8-byte pair operand per site) instead of vox + the 8-byte
+// neighbour-class cache + 32-byte unit vectors + T: the 14 class-code gathers of a warp fall into a
+// handful of 128-byte lines of a 1-byte array, a pair costs one 8-byte gather whatever its class, and
+// nothing is written but the rate sum.  DRAM traffic per refreshed site drops from ~660 B to ~190 B.
+struct CompactWarpSmem {
+    double rate[RT_WARP_PAIRS];
+    double A[32], B[32];
+    uint32_t idx[RT_WARP_PAIRS];             // local linear index of the pair's neighbour
+    uint8_t own[RT_WARP_PAIRS];              // lane that owns the pair
+};
+struct CompactSmem {
+    double tab[RT_TABLE_DOUBLES];
+    int lin[16];
+    unsigned int chunk[2];
+    CompactWarpSmem w[RT_WARPS];
+};
+struct CompactArgs {
+    const uint8_t *cvox;
+    const double *pairop, *T;
+    double *site_rate, *dep_rate;
+    const double *tab;
+    cet_rate_params P;
+    int L, n0, i_off, nloc;
+    int top_lo, top_hi;
+};
+
+__device__ __forceinline__ void compact_tile(const CompactArgs &a, const CompactSmem &sm, CompactWarpSmem &ws, int s, bool active)
+{
+    const cet_rate_params &P = a.P;
+    const int lane = threadIdx.x & 31;
+    const int L = a.L;
+    unsigned c = 0;
+    uint32_t wlo = 0, whi = 0;
+    double T_self = 1.0, T_m = 1.0, T_p = 1.0;
+    if (active) {
+        const int LL = L * L;
+        const int p = s / LL, r = s - p * LL, j = r / L, k = r - j * L;
+        const unsigned inb = inbounds_mask(a.i_off + p, j, k, a.n0, L);
+        c = a.cvox[s];
+        unsigned b[14];
+#pragma unroll
+        for (int o = 0; o < 14; ++o) b[o] = (inb >> o & 1u) ? (unsigned)a.cvox[s + sm.lin[o]] & 15u : 0u;    // 0 = outside the lattice
+#pragma unroll
+        for (int o = 0; o < 8; ++o) wlo |= b[o] << (4 * o);
+#pragma unroll
+        for (int o = 8; o < 14; ++o) whi |= b[o] << (4 * (o - 8));
+        const unsigned code = c & 15u;
+        if (code == TC_EMPTY) {
+            T_self = a.pairop[s];                                    // an empty site's pairop is its temperature
+            T_m = T_self; T_p = T_self;
+            if ((wlo | whi) & 0x11111111u) {                         // an occupied neighbour: grad_z is needed (:151-153)
+                if (k > 0) T_m = a.T[s - 1];
+                if (k < L - 1) T_p = a.T[s + 1];
+            }
+        } else if ((code & 1u) && code != TC_DEFECT) {
+            T_self = a.T[s];
+        }
+    }
+    const uint64_t w = (uint64_t)wlo | ((uint64_t)whi << 32);
+    const TilePrep q = tile_site_prep(P, sm.tab, w, active ? c : 0u, T_self, T_m, T_p);
+    const uint64_t pm = q.pm;
+    const bool is_emp = q.is_emp;
+    if (pm) { ws.A[lane] = q.A; ws.B[lane] = q.B; }
+    const int cnt = popc64(pm);
+    const unsigned mine = is_emp ? (unsigned)cnt : (unsigned)cnt << 16;
+    const unsigned all = __reduce_add_sync(0xffffffffu, mine);
+    double sum = q.sum0;
+    const int npass = all == 0 ? 0 : (((all & 0xFFFFu) + (all >> 16) > (unsigned)RT_WARP_PAIRS) ? 2 : 1);
+    for (int pass = 0; pass < npass; ++pass) {
+        const bool part = npass == 1 || (lane >> 4) == pass;
+        const unsigned mine_p = part ? mine : 0u;
+        unsigned inc = mine_p;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += u;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, inc, 31), excl = inc - mine_p;
+        const int n_att = (int)(total & 0xFFFFu), n_diff = (int)(total >> 16);
+        const int cnt_p = part ? cnt : 0;
+        const int start = is_emp ? (int)(excl & 0xFFFFu) : RT_WARP_PAIRS - (int)(excl >> 16) - cnt_p;
+        if (part) {
+            int pos = start;
+            unsigned lo = (unsigned)pm, hi = (unsigned)(pm >> 32);
+            while (lo) {
+                const int bb = __ffs(lo) - 1;
+                lo &= lo - 1;
+                ws.idx[pos] = (uint32_t)(s + sm.lin[bb >> 2]); ws.own[pos] = (uint8_t)lane; ++pos;
+            }
+            while (hi) {
+                const int bb = __ffs(hi) - 1;
+                hi &= hi - 1;
+                ws.idx[pos] = (uint32_t)(s + sm.lin[8 + (bb >> 2)]); ws.own[pos] = (uint8_t)lane; ++pos;
+            }
+        }
+        __syncwarp();
+        // pairs, 32 at a time: attachment from the front, diffusion from the back; the operand gathers of the
+        // next trip are issued before the arithmetic of the current one
+        const int qd0 = RT_WARP_PAIRS - n_diff;
+        const int n_trip = ((n_att > n_diff ? n_att : n_diff) + 31) >> 5;
+        double oa = 0.0, od = 1.0;
+        if (lane < n_att) oa = a.pairop[ws.idx[lane]];
+        if (lane < n_diff) od = a.pairop[ws.idx[qd0 + lane]];
+        for (int t = 0; t < n_trip; ++t) {
+            const int qq = 32 * t + lane, qn = qq + 32;
+            const double oa_c = oa, od_c = od;
+            if (qn < n_att) oa = a.pairop[ws.idx[qn]];
+            if (qn < n_diff) od = a.pairop[ws.idx[qd0 + qn]];
+            if (qq < n_att) {                                        // kmc_event_rates.py:135-158
+                const int ts = ws.own[qq];
+                ws.rate[qq] = att_pair_rate_E(P, oa_c, ws.A[ts], ws.B[ts], sm.tab + RT_EXP2);
+            }
+            if (qq < n_diff) {                                       // :100-109
+                const int ts = ws.own[qd0 + qq];
+                ws.rate[qd0 + qq] = diff_pair_rate(P, ws.A[ts], ws.B[ts], od_c);
+            }
+        }
+        __syncwarp();
+        for (int q0 = 0; q0 < cnt_p; ++q0) sum += ws.rate[start + q0];     // slot order: the association order of site_rate_sum
+        __syncwarp();
+    }
+    if (active) {
+        a.site_rate[s] = sum;
+        if (s >= a.top_lo && s < a.top_hi) {                             // deposition (:55-72): top plane only
+            double dep;
+            a.dep_rate[s - a.top_lo] = (is_emp && dep_rate(P, T_self, &dep)) ? dep : NAN;
+        }
+    }
+}
+
+// Queue-driven loop of one CTA over n sites (dense: s = s_lo + index; list != nullptr: s = list[index]).
+__device__ __forceinline__ void compact_cta_loop(const CompactArgs &a, CompactSmem &sm, int s_lo, int n, const int32_t *list,
+                                                 unsigned int *queue)
+{
+    for (int q = threadIdx.x; q < RT_TABLE_DOUBLES; q += blockDim.x) sm.tab[q] = a.tab[q];
+    if (threadIdx.x < 14)
+        sm.lin[threadIdx.x] = ((int)c_nb_off[threadIdx.x][0] * a.L + c_nb_off[threadIdx.x][1]) * a.L + c_nb_off[threadIdx.x][2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int CTA_CHUNK = RT_CHUNK * RT_WARPS;
+    if (threadIdx.x == 0) sm.chunk[0] = atomicAdd(queue, 1u);
+    __syncthreads();
+    for (int it = 0;; ++it) {
+        const int64_t c0 = (int64_t)sm.chunk[it & 1] * CTA_CHUNK;
+        if (c0 >= n) break;
+        if (threadIdx.x == 0) sm.chunk[(it + 1) & 1] = atomicAdd(queue, 1u);      // the next chunk, popped ahead of need
+        const int hi = (int)(c0 + CTA_CHUNK < n ? c0 + CTA_CHUNK : n);
+        for (int q0 = (int)c0 + 32 * wid; q0 < hi; q0 += 32 * RT_WARPS) {
+            const bool active = q0 + lane < hi;
+            const int s = active ? (list ? list[q0 + lane] : s_lo + q0 + lane) : 0;
+            compact_tile(a, sm, sm.w[wid], s, active);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(RT_THREADS, 5) dirty_eval_compact_kernel(const __grid_constant__ CompactArgs a, const int32_t *list,
+                                                                           const unsigned int *n_list, unsigned int *queue)
+{
+    extern __shared__ __align__(16) unsigned char rate_dyn_smem[];
+    compact_cta_loop(a, *reinterpret_cast<CompactSmem *>(rate_dyn_smem), 0, (int)*n_list, list, queue);
+}
+
+// Dense pass over local sites [s_lo, s_hi) on the compact tile state (the rebuild after a thermal step).
+__global__ void __launch_bounds__(RT_THREADS, 5) rates_compact_kernel(const __grid_constant__ CompactArgs a, int s_lo, int s_hi,
+                                                                      unsigned int *queue)
+{
+    extern __shared__ __align__(16) unsigned char rate_dyn_smem[];
+    compact_cta_loop(a, *reinterpret_cast<CompactSmem *>(rate_dyn_smem), s_lo, s_hi - s_lo, nullptr, queue);
+}
+
+static int compact_args(cet_ctx *c, CompactArgs &a)
+{
+    if (int rc = rate_tables_ensure(c)) return rc;
+    if (!c->compact_attr_set) {
+        CET_CUDA(cudaFuncSetAttribute(dirty_eval_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompactSmem)));
+        CET_CUDA(cudaFuncSetAttribute(rates_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompactSmem)));
+        c->compact_attr_set = true;
+    }
+    a.cvox = c->cvox; a.pairop = c->pairop; a.T = c->T;
+    a.site_rate = c->site_rate; a.dep_rate = c->dep_rate; a.tab = c->rate_tab;
+    a.P = c->rp;
+    a.L = (int)c->n1; a.n0 = (int)c->n0; a.i_off = (int)(c->i_begin - c->halo); a.nloc = (int)c->nloc;
+    const int64_t top = c->n0 - 1 - (c->i_begin - c->halo);
+    if (top >= 0 && top < c->np) { a.top_lo = (int)(top * c->plane); a.top_hi = (int)((top + 1) * c->plane); }
+    else { a.top_lo = 0; a.top_hi = 0; }
+    return 0;
+}
+
+// Dense evaluation of local planes [p_lo, p_hi) from cvox / pairop.
+int rates_rows_compact(cet_ctx *c, int p_lo, int p_hi)
+{
+    if (p_hi <= p_lo) return 0;
+    CompactArgs a;
+    if (int rc = compact_args(c, a)) return rc;
+    const int s_lo = (int)(p_lo * c->plane), s_hi = (int)(p_hi * c->plane);
+    unsigned int *queue = (unsigned int *)(c->rate_tab + RT_TABLE_DOUBLES);
+    CET_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned int), c->stream));
+    const int grid = (int)std::min<int64_t>(((int64_t)s_hi - s_lo + RT_CHUNK * RT_WARPS - 1) / (RT_CHUNK * RT_WARPS),
+                                            (int64_t)sm_count(c) * 5);
+    rates_compact_kernel<<<grid, RT_THREADS, sizeof(CompactSmem), c->stream>>>(a, s_lo, s_hi, queue);
+    CET_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Re-evaluate, on local planes [p_lo, p_hi), the sites whose stamp bit is set — from cvox / pairop.
+int rates_rows_dirty_compact(cet_ctx *c, int p_lo, int p_hi, const uint32_t *stamp, int32_t *list, unsigned int *counter)
+{
+    if (p_hi <= p_lo) return 0;
+    CompactArgs a;
+    if (int rc = compact_args(c, a)) return rc;
+    DirtyArgs d;
+    d.stamp = stamp; d.s_lo = (int)(p_lo * c->plane); d.s_hi = (int)(p_hi * c->plane);
+    d.list = list; d.n_list = counter;
+    const int n_words = ((d.s_hi + 31) >> 5) - (d.s_lo >> 5);
+    dirty_scan_kernel<<<(n_words + RB_WARPS * 32 - 1) / (RB_WARPS * 32), RB_WARPS * 32, 0, c->stream>>>(d);
+    CET_CUDA(cudaGetLastError());
+    const int64_t nsite = (int64_t)(p_hi - p_lo) * c->plane;
+    const int grid = (int)std::min<int64_t>((nsite + RT_CHUNK * RT_WARPS - 1) / (RT_CHUNK * RT_WARPS), (int64_t)sm_count(c) * 5);
+    unsigned int *queue = (unsigned int *)(c->rate_tab + RT_TABLE_DOUBLES) + 1;
+    CET_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned int), c->stream));
+    dirty_eval_compact_kernel<<<grid, RT_THREADS, sizeof(CompactSmem), c->stream>>>(a, list, counter, queue);
+    CET_CUDA(cudaGetLastError());
+    return 0;
 }
 
 // One warp per local plane: plane-segment sums in list order.

@@ -49,6 +49,8 @@ int tile_state_build(cet_ctx *c, int p_lo, int p_hi);
 int tile_pairop_T_update(cet_ctx *c);
 int tile_pass(cet_ctx *c, int p_lo, int p_hi, bool all);
 int stamp_fill(cet_ctx *c, int p_lo, int p_hi);
+int rates_rows_dirty_compact(cet_ctx *c, int p_lo, int p_hi, const uint32_t *stamp, int32_t *list, unsigned int *counter);
+int rates_rows_compact(cet_ctx *c, int p_lo, int p_hi);
 
 struct Record {          // one fired event
     int32_t src;         // local linear index of the source site
@@ -564,6 +566,14 @@ extern "C" int cet_sweep_set_state(cet_ctx *c, int64_t sweep_index, double tau, 
 
 namespace cet {
 
+// Refresh of the stamped sites on the compact tile state: list-driven gathers from cvox / pairop, or
+// (debug flag 32) the shared-memory tile kernel, which wins when a sweep stamps a large part of the lattice.
+static int refresh_tiled(cet_ctx *c, const SlabRanges &R)
+{
+    if (c->debug_flags & 32) return tile_pass(c, R.eval_lo, R.eval_hi, false);
+    return rates_rows_dirty_compact(c, R.eval_lo, R.eval_hi, c->stamp, c->dirty, &c->sweep->n_dirty);
+}
+
 // One sweep.  tiled: the rate sums are kept current by the TMA tile kernel (sweep_tile.cu), which needs
 // the orientation invariant of tile_state.cuh; otherwise by the gather kernels of the first design
 // (stamp scan + list-driven re-evaluation, rates.cu).  Stream, pick and apply are the same either
@@ -588,7 +598,8 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
     if (!c->sweep_rates_valid) {                     // new lattice, new T or new parameters: dense rebuild
         if (tiled && !(c->debug_flags & 8)) {
             ProfScope ps(c, PROF_RATES);
-            if (int rc = tile_pass(c, R.eval_lo, R.eval_hi, true)) return rc;
+            if (c->debug_flags & 32) { if (int rc = tile_pass(c, R.eval_lo, R.eval_hi, true)) return rc; }
+            else if (int rc = rates_rows_compact(c, R.eval_lo, R.eval_hi)) return rc;
         } else {
             if (tiled) c->nst_valid = false;         // nobody maintains the neighbour cache on the tile path
             if (int rc = nst_ensure(c)) return rc;
@@ -646,7 +657,7 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
         if (int rc = rates_rows_dirty(c, R.eval_lo, R.eval_hi, c->stamp, c->dirty, &c->sweep->n_dirty)) return rc;
     } else if (c->world == 1) {
         ProfScope ps(c, PROF_REFRESH);
-        if (int rc = tile_pass(c, R.eval_lo, R.eval_hi, false)) return rc;
+        if (int rc = refresh_tiled(c, R)) return rc;
     }
     // the totals are only needed for the next tau: reduce them here, next to the halo exchange, so
     // that a sweep has one inter-rank synchronisation point instead of two
@@ -676,7 +687,7 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
                 if (R.eval_hi > R.own_hi) if (int rc = stamp_fill(c, R.own_hi - 2, R.eval_hi)) return rc;
             }
             ProfScope ps(c, PROF_REFRESH);
-            if (int rc = tile_pass(c, R.eval_lo, R.eval_hi, false)) return rc;
+            if (int rc = refresh_tiled(c, R)) return rc;
         } else {
             ProfScope pb(c, PROF_BOUNDARY);
             c->nst_valid = true;       // the exchange marked the whole cache stale; only the planes rebuilt below are

@@ -207,11 +207,13 @@ int cet_grains_download_labels(cet_ctx *ctx, int32_t *labels);
 /* Test hook: number of sites whose cached neighbour-state word differs from a fresh gather
  * (-1 when the cache is declared stale). */
 int cet_debug_nst_mismatches(cet_ctx *ctx, int64_t *n_bad);
-/* Test / profiling hook: which kernels keep the rate sums current in cet_sweep_run.  bit 0: stage the
- * tiles of the tile kernel with cooperative loads instead of TMA; bit 1: the gather refresh of the
- * first design (stamp scan + list-driven re-evaluation) instead of the tile kernel; bit 2: the tile
- * kernel walks the 14 neighbour slots per lane instead of compacting the pairs across the warp;
- * bit 3: dense rebuilds by the gather kernel of rates.cu even when the tile kernel refreshes. */
+/* Test / profiling hook: which kernels keep the rate sums current in cet_sweep_run (all variants give
+ * the same bits).  Default: list-driven gathers from the compact tile state (class codes + pair operands).
+ * bit 1 (2): the gather refresh of the first design (neighbour-class cache + unit vectors);
+ * bit 5 (32): the shared-memory tile kernel, staged by 16-byte vector loads, or with bit 4 (16) by 3-D TMA
+ * boxes, or with bit 0 (1) by scalar loads; bit 2 (4): the tile kernel walks the 14 neighbour slots per lane
+ * instead of compacting the pairs across the warp; bit 3 (8): dense rebuilds by the gather kernel of
+ * rates.cu instead of the tile kernel. */
 int cet_debug_flags(cet_ctx *ctx, int flags);
 
 /* ---- per-kernel device timing: CUDA event pairs recorded on the context stream around every

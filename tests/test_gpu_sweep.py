@@ -1,7 +1,9 @@
 """GPU: synchronous-sublattice sweeps (csrc/sweep.cu, csrc/sweep_tile.cu) — invariants, determinism
 and level-3 parity (trajectory observables against the serial oracle within statistical bounds).
-Refresh variants (Context.debug_flags): TILE = the TMA-staged tile kernel, NO_TMA = the same kernel with
-cooperative tile loads, SERIAL = its per-lane pair loop, GATHER = the list-driven gather refresh."""
+Refresh variants (Context.debug_flags): COMPACT (default) = list-driven gathers from the compact tile state
+(class codes + pair operands); TILE = the shared-memory tile kernel (vector-load staging), TMA / SCALAR its
+other staging modes, SERIAL its per-lane pair loop; GATHER = the gather refresh of the first design
+(neighbour-class cache + unit vectors)."""
 import numpy as np
 import pytest
 
@@ -15,8 +17,9 @@ def _sweep_params(cet, seed, L, eps=0.02, p_max=0.25, defect_fraction=0.0, therm
     return sp
 
 
-TILE, SCALAR, GATHER, SERIAL, TMA = 0, 1, 2, 4, 16
-FUSED, NO_TMA = TILE, SCALAR
+COMPACT, GATHER, TILE = 0, 2, 32
+SCALAR, SERIAL, TMA = TILE | 1, TILE | 4, TILE | 16
+FUSED = COMPACT
 
 
 def _setup(cet, L, seed=3, c=0.1, flags=FUSED):
@@ -31,7 +34,7 @@ def _setup(cet, L, seed=3, c=0.1, flags=FUSED):
     return ctx, st, th, ph, T, df
 
 
-@pytest.mark.parametrize("L,flags", [(40, FUSED), (64, FUSED), (40, GATHER)])
+@pytest.mark.parametrize("L,flags", [(40, COMPACT), (64, TMA), (40, GATHER)])
 def test_sweep_is_deterministic_and_consistent(cet, L, flags):
     outs = []
     for _ in range(2):
@@ -88,7 +91,7 @@ def test_refresh_variants_agree(cet, L):
     and resident rates."""
     from cetkmc._config import thermal_params
     outs = []
-    for flags in (TILE, SCALAR, TMA, SERIAL, SERIAL | TMA, GATHER, TILE | 8):
+    for flags in (COMPACT, TILE, SCALAR, TMA, SERIAL, SERIAL | 16, GATHER, COMPACT | 8):
         ctx, st, th, ph, T, df = _setup(cet, L, flags=flags)
         res = ctx.sweep_run(7, _sweep_params(cet, 5, L, eps=0.01, p_max=0.2, defect_fraction=0.01, thermal_every=3),
                             thermal_params(1e-6, nan_to_num=True))
@@ -193,7 +196,7 @@ def test_level3_observables_vs_serial_oracle(cet, oracle):
     assert np.all(np.abs(mo - mg) <= tol), (mo, mg, tol)
 
 
-@pytest.mark.parametrize("L,flags", [(36, TILE), (64, TILE), (96, TILE), (96, SERIAL), (36, GATHER)])
+@pytest.mark.parametrize("L,flags", [(36, COMPACT), (64, COMPACT), (96, TMA), (96, SERIAL), (36, GATHER)])
 def test_resident_rates_equal_rebuild_after_sweeps(cet, L, flags):
     """Neighbour-rate refresh invariant: after N sweeps (thermal steps and defect injection
     included) the resident rate sums equal a dense rebuild by the gather kernel of rates.cu bit for
