@@ -109,6 +109,7 @@ SIGNATURES = {
     "cet_defects_refresh": [_VP, _VP, _I64, C.c_uint64, C.c_uint32, _F64, _F64, _F64, _F64, _I32, _I32, _I32,
                             C.POINTER(_I64), C.POINTER(_I64)],
     "cet_grains_label": [_VP, _F64, C.POINTER(_I64)],
+    "cet_grains_label_ex": [_VP, _F64, C.c_int, C.POINTER(_I64)],
     "cet_grains_stats": [_VP, _I64, _VP, _VP, _VP, _VP],
     "cet_grains_download_labels": [_VP, _VP],
     "cet_debug_nst_mismatches": [_VP, C.POINTER(_I64)],
@@ -403,13 +404,15 @@ class Context:
         return nc.value, nd.value
 
     # -- grains (utils.get_clusters on the resident lattice) ------------------------------------
-    def grains(self, theta_threshold=0.5, labels=False):
+    def grains(self, theta_threshold=0.5, labels=False, theta_only=False):
         """Grains of the resident lattice in the reference's cluster order (raster order of each
         grain's first voxel, utils.py:28-84).  Returns a dict: n, root (C-order site index of the
         first voxel), size (voxels), box_lo / box_hi (n, 3); with labels=True also `labels`, the
-        reference's `visited` volume (grain number 1.. per occupied site, 0 for empty)."""
+        reference's `visited` volume (grain number 1.. per occupied site, 0 for empty).
+        theta_only: the |theta1 - theta2| criterion of utils.py:49-50 instead of the misorientation."""
         n = C.c_int64(0)
-        check(lib().cet_grains_label(self._h, float(theta_threshold), C.byref(n)), "cet_grains_label")
+        check(lib().cet_grains_label_ex(self._h, float(theta_threshold), 1 if theta_only else 0, C.byref(n)),
+              "cet_grains_label_ex")
         n = n.value
         root, size = np.empty(n, np.int32), np.empty(n, np.int32)
         lo, hi = np.empty((n, 3), np.int32), np.empty((n, 3), np.int32)
@@ -432,9 +435,7 @@ class Context:
         return n.value
 
     def debug_flags(self, flags):
-        """Refresh-kernel selection of sweep_run (tests / profiling), see cet_debug_flags in cetkmc.h:
-        1 = tiles staged without TMA, 2 = gather refresh of the first design, 4 = per-lane pair loop,
-        8 = dense rebuilds by the gather kernel."""
+        """Refresh-kernel selection of sweep_run (tests / profiling); bit values in cetkmc.h (cet_debug_flags)."""
         check(lib().cet_debug_flags(self._h, int(flags)), "cet_debug_flags")
 
     def sweep_state(self):

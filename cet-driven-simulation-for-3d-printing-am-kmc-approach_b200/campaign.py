@@ -11,7 +11,8 @@
                                      (thermal_solver.update_temperature, :36-105) with a melt pool
                                      moving along axis 1 at a fixed speed — SURVEY §8d config 3
     run_gr_sweep                     config 5: independent lattices over a grid of (G, R), one per
-                                     GPU (replicas only, no communication), one cet_map.csv
+                                     GPU (replicas only, no communication), one cet_map.csv and a tree
+                                     the unmodified plot_cet.py reads (write_plot_cet_tree)
 """
 from __future__ import annotations
 
@@ -174,8 +175,8 @@ def run_cet_sublattice(L=None, n_sweeps=2000, temp=None, defect_fraction=0.0, n_
             last = sweep - 1
             if last % every == 0:                                                     # kmc_simulation.py:335-338
                 _defects.refresh_resident(ctx)
-            row, cet_detected = _ks._metrics_row(last, total_time, None, None, None, None, None, nucleation_count,
-                                                 cet_detected, consts, ctx=ctx, verbose=verbose)
+            row, cet_detected = _ks._metrics_row(last, total_time, nucleation_count, cet_detected, consts, ctx,
+                                                 verbose=verbose)
             rows.append(row)
             if checkpoint_every and (len(rows) % checkpoint_every == 0):
                 checkpoint(ctx, os.path.join(output_dir, "checkpoint"), sweep=sweep, time=total_time,
@@ -220,7 +221,25 @@ def run_gr_sweep(temps, nu_deps, L=64, n_sweeps=400, impurity_c=0.0, n_seeds=20,
                      **{k: last[k] for k in ("Step", "Time", "AspectRatio", "EquiaxedFraction", "GrainCount", "AvgGrainSize",
                                              "NucleationCount", "CET_Class", "CET_Detected")}})
     _write_rows(rows, os.path.join(out_dir, f"cet_map_rank{rank}.csv"))
+    write_plot_cet_tree([(r["case"], f"outputs/{output_root}/T{r['T_sub']:g}_R{r['NU_DEP']:g}/metrics.csv") for r in rows],
+                        os.path.join(out_dir, "plot_cet"))
     return rows
+
+
+def write_plot_cet_tree(cases, root):
+    """Lay per-case metrics files out the way the reference's plot_cet.py discovers them
+    (plot_cet.py:26: `outputs/impurity_c_<id>/metrics_<id>.csv` below the working directory; it
+    labels a series "<id>% C", reads Step / AspectRatio / DefectDensity / EquiaxedFraction, :49-71):
+    `<root>/outputs/impurity_c_<id>/metrics_<id>.csv` for every (id, path of a metrics.csv) in `cases`.
+    Run the unmodified script from `<root>`: `cd <root> && python /path/to/plot_cet.py`; for a G-R
+    sweep the id is the case number of cet_map.csv (which holds its T_sub, NU_DEP, G and R).  Every
+    rank of a sweep adds its own cases."""
+    import shutil
+    for cid, path in cases:
+        d = os.path.join(root, "outputs", f"impurity_c_{int(cid)}")
+        os.makedirs(d, exist_ok=True)
+        shutil.copyfile(path, os.path.join(d, f"metrics_{int(cid)}.csv"))
+    return root
 
 
 def _write_rows(rows, path):

@@ -47,15 +47,19 @@ __global__ void grains_init_kernel(const uint8_t *__restrict__ vox, int *label, 
 }
 
 // offsets 0,1,4,5,8,10,12 are one of each +/- pair of the neighbour table
-__global__ void grains_union_kernel(const uint8_t *__restrict__ vox, const Vec4 *__restrict__ v, int *label, int L,
-                                    int p_lo, int p_hi, double cos_thr)
+// theta == nullptr: edge iff clamp(v1.v2) > thr (thr = cos of the misorientation threshold);
+// theta != nullptr: the |theta1 - theta2| < thr criterion of utils.py:49-50 (orientation_phi=None).
+__global__ void grains_union_kernel(const uint8_t *__restrict__ vox, const Vec4 *__restrict__ v, const double *__restrict__ theta,
+                                    int *label, int L, int p_lo, int p_hi, double thr)
 {
     const int LL = L * L;
     const int64_t lo = (int64_t)p_lo * LL, hi = (int64_t)p_hi * LL;
     for (int64_t s = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < hi; s += (int64_t)gridDim.x * blockDim.x) {
         if ((vox[s] & 0x0F) == 0) continue;
         const int p = (int)(s / LL), j = (int)((s / L) % L), k = (int)(s % L);
-        const Vec4 a = v[s];
+        Vec4 a = Vec4{0.0, 0.0, 0.0, 0.0};
+        double ta = 0.0;
+        if (theta) ta = theta[s]; else a = v[s];
         const int pos[7] = {0, 1, 4, 5, 8, 10, 12};
 #pragma unroll
         for (int q = 0; q < 7; ++q) {
@@ -64,10 +68,16 @@ __global__ void grains_union_kernel(const uint8_t *__restrict__ vox, const Vec4 
             if (pi < p_lo || pi >= p_hi || nj < 0 || nj >= L || nk < 0 || nk >= L) continue;
             const int64_t t = s + ((int64_t)CET_NB_DI(o) * L + CET_NB_DJ(o)) * L + CET_NB_DK(o);
             if ((vox[t] & 0x0F) == 0) continue;
-            const Vec4 b = v[t];
-            double dot = a.x * b.x + a.y * b.y + a.z * b.z;
-            dot = pymax(pymin(dot, 1.0), -1.0);
-            if (dot > cos_thr) uf_union(label, (int)s, (int)t);
+            bool edge;
+            if (theta) {
+                edge = fabs(ta - theta[t]) < thr;
+            } else {
+                const Vec4 b = v[t];
+                double dot = a.x * b.x + a.y * b.y + a.z * b.z;
+                dot = pymax(pymin(dot, 1.0), -1.0);
+                edge = dot > thr;
+            }
+            if (edge) uf_union(label, (int)s, (int)t);
         }
     }
 }
@@ -137,9 +147,18 @@ extern "C" {
 
 // utils.get_clusters (utils.py:69-84) on the resident lattice: label the grains of the owned
 // planes.  n_grains receives the number of components.
+int cet_grains_label_ex(cet_ctx *c, double theta_threshold, int criterion, int64_t *n_grains);
 int cet_grains_label(cet_ctx *c, double theta_threshold, int64_t *n_grains)
 {
+    return cet_grains_label_ex(c, theta_threshold, 0, n_grains);
+}
+
+// criterion 0: misorientation of the orientation vectors < threshold (utils.py:51-56, what metrics.py uses);
+// criterion 1: |theta1 - theta2| < threshold (utils.py:49-50, get_clusters(..., orientation_phi=None)).
+int cet_grains_label_ex(cet_ctx *c, double theta_threshold, int criterion, int64_t *n_grains)
+{
     CET_REQUIRE(c && n_grains && c->cubic, "cet_grains_label: bad argument");
+    CET_REQUIRE(criterion == 0 || criterion == 1, "cet_grains_label: unknown criterion %d", criterion);
     CET_REQUIRE(c->nloc < (1ll << 31), "cet_grains_label: the local lattice must have fewer than 2^31 sites");
     CET_REQUIRE(c->world == 1 && c->halo == 0, "cet_grains_label: grains are labelled on a whole lattice (one context)");
     cet::DeviceGuard dg(c->device);
@@ -151,8 +170,8 @@ int cet_grains_label(cet_ctx *c, double theta_threshold, int64_t *n_grains)
     const int64_t lo = 0, hi = c->nloc;
     const int grid = (int)std::min<int64_t>((hi + 255) / 256, (int64_t)sm_count(c) * 16);
     grains_init_kernel<<<grid, 256, 0, c->stream>>>(c->vox, c->grain_label, lo, hi);
-    grains_union_kernel<<<grid, 256, 0, c->stream>>>(c->vox, c->v, c->grain_label, (int)c->n1, 0, (int)c->np,
-                                                     cos(theta_threshold));
+    grains_union_kernel<<<grid, 256, 0, c->stream>>>(c->vox, c->v, criterion == 1 ? c->theta : nullptr, c->grain_label, (int)c->n1, 0,
+                                                     (int)c->np, criterion == 1 ? theta_threshold : cos(theta_threshold));
     grains_flatten_kernel<<<grid, 256, 0, c->stream>>>(c->grain_label, c->grain_gid, lo, hi, cnt);
     CET_CUDA(cudaGetLastError());
     unsigned int h = 0;

@@ -39,16 +39,9 @@ except Exception:                                         # noqa: BLE001
     introduce_defects = _host.introduce_defects
 from . import defects as _gpu_defects                     # the 200-step mask refresh runs on the resident lattice
 # Observables: grains are clustered on the GPU from the resident lattice (csrc/grains.cu).
-# CETKMC_METRICS=host selects the NumPy/SciPy restatement in _host.py, CETKMC_METRICS=reference
-# the caller's own metrics.py (pure-Python DFS, utils.py:28-84).
 from . import metrics as _gpu_metrics
-_METRICS_MODE = os.environ.get("CETKMC_METRICS", "gpu")
-if _METRICS_MODE == "reference":
-    from metrics import compute_metrics, detect_CET_transition   # type: ignore
-elif _METRICS_MODE == "host":
-    compute_metrics, detect_CET_transition = _host.compute_metrics, _host.detect_CET_transition
-else:
-    compute_metrics, detect_CET_transition = _gpu_metrics.compute_metrics, _gpu_metrics.detect_CET_transition
+compute_metrics, compute_CET, detect_CET_transition = (_gpu_metrics.compute_metrics, _gpu_metrics.compute_CET,
+                                                       _gpu_metrics.detect_CET_transition)   # kmc_simulation.py:194
 
 LATTICE_SIZE = constants.LATTICE_SIZE
 N_STEPS = constants.N_STEPS
@@ -64,21 +57,14 @@ def _replay(stream_state_setter, state, draw, n):
     draw(n)
 
 
-def _metrics_row(step, total_time, state, atom_type, theta, phi, defects_mask, nucleation_count,
-                 cet_detected, consts, ctx=None, verbose=True):
-    """kmc_simulation.py:341-378 — one metrics.csv row."""
+def _metrics_row(step, total_time, nucleation_count, cet_detected, consts, ctx, verbose=True):
+    """kmc_simulation.py:341-378 — one metrics.csv row, from the lattice resident in `ctx`."""
     G, R, R_phys, G_over_R_phys = consts
-    if ctx is not None and _METRICS_MODE == "gpu":
-        counts = ctx.counts()
-        n_sites = int(np.prod(ctx.owned_shape))
-        m = _gpu_metrics.metrics_from_grains(ctx.grains(0.5), n_sites, voxel_size=constants.VOXEL_SIZE)
-        n_w, n_re, n_c = int(counts[1]), int(counts[2]), int(counts[3])
-        defect_voxels = int(counts[constants.DEFECT_ID])
-    else:
-        m = compute_metrics(state, theta, phi, defects=defects_mask, voxel_size=constants.VOXEL_SIZE)
-        n_w, n_re, n_c = int((state == 1).sum()), int((state == 2).sum()), int((state == 3).sum())
-        defect_voxels = int(np.sum(atom_type == constants.DEFECT_ID))
-        n_sites = atom_type.size
+    counts = ctx.counts()
+    n_sites = int(np.prod(ctx.owned_shape))
+    m = _gpu_metrics.metrics_from_grains(ctx.grains(0.5), n_sites, voxel_size=constants.VOXEL_SIZE)
+    n_w, n_re, n_c = int(counts[1]), int(counts[2]), int(counts[3])
+    defect_voxels = int(counts[constants.DEFECT_ID])
     m["Defect_voxel_count"] = defect_voxels
     m["DefectDensity"] = float(defect_voxels / n_sites)
     newly = (not cet_detected) and detect_CET_transition(m)
@@ -202,20 +188,11 @@ def run_kmc(L: int = LATTICE_SIZE, n_steps: int = N_STEPS, temp: float = T_SUB,
                 terminated = True
                 break
             last_step = step - 1
-            if _METRICS_MODE == "gpu":
-                # resident cadence (kmc_simulation.py:335-389): the mask refresh, the clustering and the
-                # species counts all run on the device; nothing but the row's scalars crosses PCIe
-                if last_step % every == 0:                                            # :335-338
-                    _gpu_defects.refresh_resident(ctx)
-                row, cet_detected = _metrics_row(last_step, total_time, None, None, None, None, None,
-                                                 nucleation_count, cet_detected, consts, ctx=ctx)
-            else:
-                ctx.download(out=dict(state=state, atom_type=atom_type, theta=theta, phi=phi, T=T))
-                if last_step % every == 0:                                            # :335-338
-                    defects_mask, _ = introduce_defects(state, atom_type, T, apply_to_state=False)
-                    ctx.upload(defects=defects_mask)
-                row, cet_detected = _metrics_row(last_step, total_time, state, atom_type, theta, phi,
-                                                 defects_mask, nucleation_count, cet_detected, consts, ctx=ctx)
+            # resident cadence (kmc_simulation.py:335-389): the mask refresh, the clustering and the
+            # species counts all run on the device; nothing but the row's scalars crosses PCIe
+            if last_step % every == 0:                                                # :335-338
+                _gpu_defects.refresh_resident(ctx)
+            row, cet_detected = _metrics_row(last_step, total_time, nucleation_count, cet_detected, consts, ctx)
             rows.append(row)
         ctx.download(out=dict(state=state, atom_type=atom_type, theta=theta, phi=phi, T=T))
         if terminated:

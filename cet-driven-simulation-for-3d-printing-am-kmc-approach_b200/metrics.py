@@ -129,21 +129,17 @@ def get_clusters(state, orientation_theta, orientation_phi=None, theta_threshold
     of their first voxel) and `visited` is the reference's label volume; inside a cluster the
     voxels are listed in raster order (the reference lists them in DFS order; its consumers —
     len() and the bounding box — do not depend on it).  orientation_phi=None selects the
-    reference's |theta1 - theta2| criterion, which only the unused detect_CET_transition of
-    utils.py:117 takes; it is evaluated on the host."""
+    reference's |theta1 - theta2| criterion (utils.py:49-50), which only the unused
+    detect_CET_transition of utils.py:117 takes."""
     state = np.asarray(state)
     if state.size == 0:
         return [], np.array([])
-    if orientation_phi is None:
-        from ._host import label_grains
-        visited, n = label_grains(state, orientation_theta, None, theta_threshold)
-    else:
-        ctx = _resident(state, orientation_theta, orientation_phi, device)
-        try:
-            g = ctx.grains(theta_threshold, labels=True)
-        finally:
-            ctx.close()
-        visited, n = g["labels"], g["n"]
+    ctx = _resident(state, orientation_theta, orientation_phi, device)
+    try:
+        g = ctx.grains(theta_threshold, labels=True, theta_only=orientation_phi is None)
+    finally:
+        ctx.close()
+    visited, n = g["labels"], g["n"]
     flat = visited.ravel()
     occ = np.flatnonzero(flat)
     order = np.argsort(flat[occ], kind="stable")

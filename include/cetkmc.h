@@ -197,6 +197,9 @@ int cet_defects_refresh(cet_ctx *ctx, const double *draws, int64_t n_draws, uint
  * Grains = connected components of occupied sites (state != 0) joined by the 14-offset
  * neighbourhood with misorientation < theta_threshold.  Whole-lattice contexts only. */
 int cet_grains_label(cet_ctx *ctx, double theta_threshold, int64_t *n_grains);
+/* criterion 0: misorientation of the orientation vectors < threshold (utils.py:51-56; cet_grains_label);
+ * criterion 1: |theta1 - theta2| < threshold (utils.py:49-50, get_clusters(..., orientation_phi=None)). */
+int cet_grains_label_ex(cet_ctx *ctx, double theta_threshold, int criterion, int64_t *n_grains);
 /* Per grain (arbitrary order; sort by root for the reference's cluster order): root = smallest
  * C-order site index (the grain's first voxel), voxel count, bounding box lo/hi [3*g + axis]. */
 int cet_grains_stats(cet_ctx *ctx, int64_t cap, int32_t *root, int32_t *size, int32_t *box_lo,

@@ -1,0 +1,7 @@
+from matplotlib import _Any
+
+
+def __getattr__(name):
+    if name.startswith("__") and name.endswith("__"):
+        raise AttributeError(name)
+    return _Any()

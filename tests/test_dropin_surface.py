@@ -76,9 +76,9 @@ print("ok")
 
 @need_ref
 def test_host_metrics_match_reference(oracle):
-    """_host.compute_metrics (graph connected components) == the reference's DFS clustering."""
+    """hostref.compute_metrics (graph connected components) == the reference's DFS clustering."""
     import numpy as np
-    from cetkmc import _host
+    import hostref as _host
     ref = refharness.load()
     for seed, L in ((1, 10), (2, 12)):
         st, th, ph, T, df = oracle.half_grown_lattice(L, seed=seed, grain=3)

@@ -154,46 +154,124 @@ def test_diffusion_only_conserves_atoms(cet):
     np.testing.assert_array_equal(np.sort(f["theta"][f["state"] > 0]), np.sort(th[st > 0]))
 
 
-def test_level3_observables_vs_serial_oracle(cet, oracle):
-    """Level-3 parity: over N seeds, the sublattice path and the serial oracle, run to the same
-    number of executed events from the same initial lattice, agree on occupied fraction, grain
-    count, Re fraction, equiaxed fraction and mean grain aspect ratio within 4 standard errors + 3 %
-    of the mean."""
-    from cetkmc import _host
-    from cetkmc._config import rate_params
-    L, n_events, n_seeds, c = 16, 1500, 6, 0.1
-    obs_o, obs_g = [], []
-    for seed in range(n_seeds):
-        st, th, ph, T, at = oracle.initialize_lattice(L, n_seeds=8, random_seed=seed, impurity_c=c)
+LEVEL3_K = 4.0          # tolerance of the level-3 comparison, in standard errors of the difference of the two ensemble means
+L3 = dict(L=30, n_seeds=16, c=0.1, defect_fraction=3e-3, checkpoints=(500, 1000, 1500, 2000))
+L3_NAMES = ("EquiaxedFraction", "GrainCount", "AspectRatio", "occupied", "Re fraction")
+
+
+def _l3_observe(m, state):
+    occ = int((state != 0).sum())
+    return [m["EquiaxedFraction"], m["GrainCount"], m["AspectRatio"], occ, (state == 2).sum() / max(occ, 1)]
+
+
+@pytest.fixture(scope="module")
+def l3_oracle(oracle):
+    """The serial side of level 3: oracle.kmc_run (kmc_simulation.py:246-332, thermal every 20 steps,
+    defect injection) on 16 seeded main.py-default lattices; observables by the host restatement."""
+    import hostref
+    L, c = L3["L"], L3["c"]
+    n_events = L3["checkpoints"][-1]
+    obs, cet_pos, lattices = [], [], []
+    for seed in range(L3["n_seeds"]):
+        st, th, ph, T, at = oracle.initialize_lattice(L, n_seeds=20, random_seed=seed, impurity_c=c)
+        lattices.append((st, th, ph, T))
         df = np.zeros_like(st)
-        d = oracle.DrawStreams(seed=seed, n_py=2 * n_events, n_np=2 * n_events, n_sp=n_events * L * L)
+        d = oracle.DrawStreams(seed=seed, n_py=3 * n_events, n_np=2 * n_events, n_sp=n_events * L * L)
         o = [a.copy() for a in (st, at, th, ph, T)]
-        tp = oracle.make_thermal_params()
-        tp.every = 10 ** 9
-        r = oracle.kmc_run(o[0], o[1], o[2], o[3], o[4], df, L, oracle.make_params(c), 1, n_events, 0.0,
-                           d.py, d.np, d.sp, thermal=tp, log=False)
-        assert r["steps_done"] == n_events
-        m = _host.compute_metrics(o[0], o[2], o[3])
-        obs_o.append([(o[0] != 0).sum(), m["GrainCount"], (o[0] == 2).sum() / max((o[0] != 0).sum(), 1),
-                      m["EquiaxedFraction"], m["AspectRatio"]])
+        pos, first, done = [0, 0, 0], -1, 0
+        for cp in L3["checkpoints"]:
+            r = oracle.kmc_run(o[0], o[1], o[2], o[3], o[4], df, L, oracle.make_params(c), done, cp - done,
+                               L3["defect_fraction"], d.py[pos[0]:], d.np[pos[1]:], d.sp[pos[2]:],
+                               thermal=oracle.make_thermal_params(), log=False)
+            assert r["steps_done"] == cp - done
+            pos = [pos[0] + r["py_used"], pos[1] + r["np_used"], pos[2] + r["sp_used"]]
+            done = cp
+            m = hostref.compute_metrics(o[0], o[2], o[3])
+            if first < 0 and hostref.detect_CET_transition(m):
+                first = cp
+        obs.append(_l3_observe(m, o[0])); cet_pos.append(first)
+    return lattices, np.array(obs, dtype=float), np.array(cet_pos, dtype=float)
+
+
+def _l3_sublattice(cet, lattices, events_per_sweep):
+    """The sublattice side: same lattices, one thermal update per 20 EXECUTED events, observables from
+    the GPU clustering (Context.grains)."""
+    from cetkmc import metrics as M
+    from cetkmc._config import rate_params, thermal_params
+    L, c = L3["L"], L3["c"]
+    n_events = L3["checkpoints"][-1]
+    obs, cet_pos, over = [], [], []
+    for seed, (st, th, ph, T) in enumerate(lattices):
         ctx = cet.Context(L=L)
         ctx.set_rate_params(rate_params(c))
-        ctx.upload(state=st, theta=th, phi=ph, T=T, defects=df)
-        sp = _sweep_params(cet, 1000 + seed, L, eps=n_events / 60 / L ** 3, p_max=0.1)
-        applied = 0
-        while applied < n_events:
-            applied += ctx.sweep_run(1, sp, None)["events_applied"]
-        f = ctx.download(state=True, theta=True, phi=True)
+        ctx.upload(state=st, theta=th, phi=ph, T=T, defects=np.zeros_like(st))
+        sp = _sweep_params(cet, 1000 + seed, L, eps=events_per_sweep / L ** 3, p_max=0.1,
+                           defect_fraction=L3["defect_fraction"], thermal_every=0)
+        tp = thermal_params(1e-6, nan_to_num=True)
+        applied, first, n_thermal = 0, -1, 0
+        for cp in L3["checkpoints"]:
+            while applied < cp:
+                while n_thermal <= applied // 20:            # steps 0, 20, 40, ... of the reference (kmc_simulation.py:248)
+                    ctx.thermal_cet(tp)
+                    n_thermal += 1
+                applied += ctx.sweep_run(1, sp, None)["events_applied"]
+            m = M.metrics_from_grains(ctx.grains(0.5), L ** 3)
+            if first < 0 and M.detect_CET_transition(m):
+                first = cp
+        f = ctx.download(state=True)
         ctx.close()
-        m = _host.compute_metrics(f["state"], f["theta"], f["phi"])
-        scale = n_events / applied                   # the last sweep overshoots by a few events
-        obs_g.append([(f["state"] != 0).sum() * scale, m["GrainCount"] * scale,
-                      (f["state"] == 2).sum() / max((f["state"] != 0).sum(), 1), m["EquiaxedFraction"], m["AspectRatio"]])
-    obs_o, obs_g = np.array(obs_o, dtype=float), np.array(obs_g, dtype=float)
+        obs.append(_l3_observe(m, f["state"])); cet_pos.append(first); over.append(applied - n_events)
+    return np.array(obs, dtype=float), np.array(cet_pos, dtype=float), np.array(over, dtype=float)
+
+
+def test_level3_observables_vs_serial_oracle(cet, l3_oracle):
+    """Level-3 parity at the main.py default (BASELINE configs[0]: L = 30, n_seeds = 20,
+    defect_fraction = 3e-3, thermal update every 20 events, kmc_simulation.py:248): over N = 16 seeds
+    the sublattice path and the serial oracle, started from the same initial lattices and compared at
+    the same number of executed events, agree on the north-star observables
+        equiaxed fraction, grain count, mean grain aspect ratio, CET position
+    (CET position = the first checkpoint at which detect_CET_transition holds, metrics.py:103-105,
+    checked every 500 events; -1 = never) and on the occupied count and Re fraction, within
+    LEVEL3_K standard errors of the difference of the means (no additive slack).
+
+    Matching conventions, stated because the two algorithms are not step-for-step comparable:
+      * events: 4 events per sweep (0.015 % of the sites).  The synchronous sweep is a first-order
+        approximation in the sweep interval; its bias against the serial algorithm at larger sweeps is
+        measured, not assumed away (test_level3_bias_at_the_benchmark_setting);
+      * thermal: the stencil is driven from the host once per 20 EXECUTED events like the reference's
+        `step % 20 == 0` — not once per sweep: when the unstable stencil has produced sites above T_MELT
+         the p_max cap shortens the sweeps to a few events each, and a per-sweep cadence
+        would advance the temperature field several times faster per event than the reference does;
+      * time: the reference's clock is dt = max(-ln u / R, 1e-12) with R ~ 1e17..1e18 s^-1, so the floor
+        always wins and Time == 1e-12 s x events — equal event counts ARE equal reference
+        times; the sublattice path's own clock (sum of tau) is physical and not comparable."""
+    lattices, obs_o, cet_o = l3_oracle
+    obs_g, cet_g, over = _l3_sublattice(cet, lattices, 4.0)
+    n = L3["n_seeds"]
+    assert over.max() < 20                                   # the last sweep overshoots by a few events at most
     mo, mg = obs_o.mean(0), obs_g.mean(0)
-    se = np.sqrt(obs_o.var(0, ddof=1) / n_seeds + obs_g.var(0, ddof=1) / n_seeds)
-    tol = 4 * se + 0.03 * np.abs(mo) + 1e-9
-    assert np.all(np.abs(mo - mg) <= tol), (mo, mg, tol)
+    se = np.sqrt(obs_o.var(0, ddof=1) / n + obs_g.var(0, ddof=1) / n)
+    report = {k: (round(a, 4), round(b, 4), round(e, 4)) for k, a, b, e in zip(L3_NAMES, mo, mg, se)}
+    assert np.all(np.abs(mo - mg) <= LEVEL3_K * se + 1e-12), report
+    se_c = np.sqrt(cet_o.var(ddof=1) / n + cet_g.var(ddof=1) / n)
+    assert abs(cet_o.mean() - cet_g.mean()) <= LEVEL3_K * se_c + 1e-12, (cet_o, cet_g)
+
+
+def test_level3_bias_at_the_benchmark_setting(cet, l3_oracle):
+    """The throughput benchmark fires 0.5 % of the sites per sweep (bench.py).  At that setting the
+    synchronous sweeps are a coarser approximation of the serial algorithm: this test MEASURES the
+    bias of the same observables on the same ensemble and bounds it — relative deviation of the
+    ensemble means <= 8 % for the counts, <= 0.03 absolute for the equiaxed fraction and the aspect
+    ratio, CET position unchanged (profiles/ records the measured values)."""
+    lattices, obs_o, cet_o = l3_oracle
+    obs_g, cet_g, over = _l3_sublattice(cet, lattices, 0.005 * L3["L"] ** 3)
+    mo, mg = obs_o.mean(0), obs_g.mean(0)
+    scale = L3["checkpoints"][-1] / (L3["checkpoints"][-1] + over.mean())      # the last sweep overshoots by ~half a sweep
+    report = {k: (round(a, 4), round(b, 4)) for k, a, b in zip(L3_NAMES, mo, mg)}
+    print("level-3 bias at 0.5 % per sweep:", report, "overshoot", over.mean())
+    assert abs(mg[0] - mo[0]) <= 0.03 and abs(mg[2] - mo[2]) <= 0.03, report
+    assert abs(mg[1] * scale / mo[1] - 1) <= 0.08 and abs(mg[3] * scale / mo[3] - 1) <= 0.08, report
+    assert cet_o.mean() == cet_g.mean(), (cet_o, cet_g)
 
 
 @pytest.mark.parametrize("L,flags", [(36, COMPACT), (64, COMPACT), (96, TMA), (96, SERIAL), (36, GATHER)])
