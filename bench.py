@@ -2,6 +2,7 @@
 """bench.py — KMC site-updates/s of the sublattice sweep on the 512^3 lattice (BASELINE.json).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cetkmc|reference]
+                    [--scaling strong|weak] [--L 512] [--thermal cet|laser]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 One step = one synchronous-sublattice sweep over the whole lattice (csrc/sweep.cu): thermal stencil
@@ -9,12 +10,20 @@ One step = one synchronous-sublattice sweep over the whole lattice (csrc/sweep.c
 against its resident rate sum, event pick + conflict resolution + apply for the fired sites,
 neighbour-rate refresh of the sites the events touched, totals for the next time increment, and
 (N > 1) the halo exchange.
-Workload: the 'half-grown' synthetic lattice of SURVEY §8(d)(ii), 512 x 512 x 512 sites per GPU;
-N GPUs hold a (512 N) x 512 x 512 lattice split into z-slabs (weak scaling).
+Workload: the 'half-grown' synthetic lattice of SURVEY §8(d)(ii).
+    default / --scaling strong : the lattice the metric names, L^3 = 512^3, split into z-slabs over
+                                 the N GPUs (BASELINE.json: "512^3 at 1/2/4/8 B200"); --L 1024 is
+                                 BASELINE configs[3]
+    --scaling weak             : N GPUs hold (L N) x L x L, L planes each
+    --thermal laser            : BASELINE configs[2] — the thermal step is thermal_solver.update_temperature
+                                 (laser source + latent heat, thermal_solver.py:36-105) with the melt pool
+                                 moving along axis 1, driven between 20-sweep blocks (N = 1)
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract: roofline (dominant kernel, live
-CUDA-event timing), cpu_baseline (the oracle port on the host cores, bounded sample), e2e (the
-public API call with host buffers, copies inside the timed region), clocks, gpu_launches.
+CUDA-event timing), roofline_all, cpu_baseline (the oracle port on the host cores, bounded sample),
+e2e (the sweep API call with host buffers, copies inside the timed region), api_e2e (the reference-
+signature calls run_kmc / update_temperature_cet / get_event_rates, host arrays in, host arrays out),
+clocks, gpu_launches.
 """
 import argparse
 import json
@@ -31,14 +40,17 @@ sys.path.insert(0, ROOT)
 
 L_BENCH = 512
 THERMAL_EVERY = 20
-EVENTS_FRACTION = 0.005         # events_per_sweep = 0.5 % of the sites (the level-3 parity tests run at <= this)
+EVENTS_FRACTION = 0.005         # events_per_sweep = 0.5 % of the sites (fidelity at this setting: tests/test_gpu_sweep.py, level 3)
 P_MAX = 0.1
-# algorithmic bytes per unit of each dense kernel
+# Algorithmic bytes per unit.  The contract figure of the rate evaluation is
+# 33 B/site (1 B state + 8 B theta + 8 B phi + 8 B T read, 8 B rate sum written); the resident layout the
+# kernels read is listed beside it as bytes_layout.
 BYTES_STREAM = 8                # resident rate sum read once per site
-BYTES_RATES = 41                # 1 B state + 8 B T + 24 B unit vector read, 8 B rate sum written
-BYTES_STAMP = 1                 # refresh scan: one stamp byte per site
+BYTES_RATES = 33
+BYTES_RATES_LAYOUT = 25         # compact tile state: 1 B class code + 8 B pair operand + 8 B T read, 8 B written
+BYTES_STAMP = 1.0 / 8.0         # refresh scan: one stamp BIT per site
 BYTES_THERMAL = 16              # T read + T written
-CPU_SAMPLE_L = 160              # cpu_baseline / reference arm: one 160^3 block of the same workload
+CPU_SAMPLE_L = 160              # cpu_baseline leg of the GPU arm: one 160^3 block of the same workload (~10 s)
 
 
 def peaks():
@@ -92,15 +104,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _oracle(threads):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    O.build()
+    return O
+
+
 def cpu_rate_sample(threads):
     """The oracle port (oracle/oracle.c, OpenMP over planes) evaluating every event rate of a
     CPU_SAMPLE_L^3 block of the benchmark workload — the reference's get_event_rates sweep, which
     is what one 'site-update' costs on the CPU path (kmc_simulation.py:253)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as O
+    O = _oracle(threads)
     from cetkmc import _synth
-    os.environ["OMP_NUM_THREADS"] = str(threads)
-    O.build()
     Ls = CPU_SAMPLE_L
     packed, th, ph, T = _synth.half_grown(Ls, seed=1234)
     st, df = _synth.unpack(packed)
@@ -116,34 +133,49 @@ def cpu_rate_sample(threads):
     return Ls ** 3 * reps / dt, dt, reps
 
 
+def workload_name(args, world):
+    L = args.L
+    if args.scaling == "weak":
+        shape = f"{L * world}x{L}x{L} ({L} planes per GPU)"
+    else:
+        shape = f"{L}x{L}x{L}" + (f" split into {world} z-slabs" if world > 1 else "")
+    therm = ("update_temperature_cet" if args.thermal == "cet" else "update_temperature with a moving laser source")
+    return (f"half-grown lattice {shape} (SURVEY 8d-ii: 25% solid, salt-and-pepper below a wavy front, linear G), "
+            f"synchronous-sublattice sweeps with resident rates + neighbour-rate refresh, {therm} and dense rate "
+            f"rebuild every {THERMAL_EVERY} sweeps, events_per_sweep={EVENTS_FRACTION}N, p_max={P_MAX}, defect_fraction=3e-3")
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm for this path (oracle port; the Python
-    reference cannot travel to the GPU box) on all host threads, bounded sample per step."""
+    """--impl reference: the reference's CPU algorithm for this path on all host threads.  The
+    reference is pure Python / Numba and cannot travel to the GPU box (the tier forbids shipping its
+    sources), so this arm times its C restatement (oracle/oracle.c, OpenMP, pinned bit-exact to the
+    reference by tests/) on the SAME lattice the GPU arm sweeps at N = 1: one step = one full
+    get_event_rates evaluation of the half-grown L^3 lattice — what every executed event of the
+    reference's loop costs (kmc_simulation.py:253).  For scale: the reference's own single-thread
+    Numba path measured 3.4e5 sites/s in the build container, ~200x below this port."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as O
+    O = _oracle(threads)
     from cetkmc import _synth
-    os.environ["OMP_NUM_THREADS"] = str(threads)
-    O.build()
-    Ls = CPU_SAMPLE_L
+    Ls = args.L
     packed, th, ph, T = _synth.half_grown(Ls, seed=1234)
     st, df = _synth.unpack(packed)
+    del packed
     p = O.make_params(0.1)
-    for _ in range(max(args.warmup, 1)):
+    for _ in range(max(min(args.warmup, 3), 1)):
         O.site_rates(st, th, ph, T, df, Ls, p)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         O.site_rates(st, th, ph, T, df, Ls, p)        # one full rate sweep = one visit of every site
     dt = time.perf_counter() - t0
     value = Ls ** 3 * args.steps / dt
-    sample = f"{Ls}^3 block of the half-grown workload, one full event-rate sweep per step (oracle.c, OpenMP)"
+    sample = f"the whole half-grown {Ls}^3 lattice, one full event-rate evaluation per step (oracle.c, OpenMP, {threads} threads)"
     print(json.dumps({
         "impl": "reference", "metric": "kmc_site_updates_per_s", "value": value, "unit": "site-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"half-grown {L_BENCH}^3 per GPU (reference arm: {sample})"},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args, 1)},
         "cpu_baseline": {"value": value, "unit": "site-updates/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "site-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -153,10 +185,55 @@ def pinned(shape, dtype):
     """Page-locked host array (torch allocator) — falls back to pageable memory."""
     try:
         import torch
-        t = torch.empty(tuple(shape), dtype={np.float64: torch.float64, np.uint8: torch.uint8}[dtype], pin_memory=True)
+        t = torch.empty(tuple(shape), dtype={np.float64: torch.float64, np.uint8: torch.uint8, np.int64: torch.int64}[dtype],
+                        pin_memory=True)
         return t.numpy(), t
     except Exception:
         return np.empty(shape, dtype=dtype), None
+
+
+def api_e2e():
+    """The reference-signature calls (host NumPy arrays in, host NumPy arrays out), wall clock around
+    the call as a user makes it: run_kmc at the main.py default lattice, update_temperature_cet at
+    512^3, get_event_rates at 128^3 (BASELINE configs[0..1])."""
+    import io
+    import tempfile
+    from cetkmc import _synth, kmc_event_rates, kmc_simulation, thermal_solver
+    out = {}
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        stdout, sys.stdout = sys.stdout, io.StringIO()
+        try:
+            kw = dict(L=30, temp=2800, defect_fraction=3e-3, n_seeds=20, impurity_c=0.1, output_prefix="bench")
+            kmc_simulation.run_kmc(n_steps=201, **kw)                   # warm-up (library load, first launches)
+            t0 = time.perf_counter()
+            kmc_simulation.run_kmc(n_steps=4001, **kw)
+            dt = time.perf_counter() - t0
+        finally:
+            sys.stdout = stdout
+            os.chdir(cwd)
+    out["run_kmc_L30"] = {"value": 4001 / dt, "unit": "KMC steps/s",
+                          "what": "run_kmc(L=30, n_steps=4001, defect_fraction=3e-3, n_seeds=20, impurity_c=0.1) incl. lattice "
+                                  "set-up, metrics rows and CSV; reference: 11.7 steps/s (BASELINE.md)"}
+    T = np.ascontiguousarray(np.broadcast_to(2800.0 + 895.0 * np.arange(512) / 512, (512, 512, 512)))
+    thermal_solver.update_temperature_cet(T[:64], None, dt=1e-6)
+    t0 = time.perf_counter()
+    T2 = thermal_solver.update_temperature_cet(T, None, dt=1e-6)
+    dt = time.perf_counter() - t0
+    out["update_temperature_cet_512"] = {"value": T.size / dt, "unit": "sites/s", "h2d_bytes": T.nbytes, "d2h_bytes": T2.nbytes,
+                                         "what": "one call, (512,512,512) float64 host array in, new host array out (pageable "
+                                                 "memory, as a caller of the reference holds it); reference: 1.6e7 sites/s"}
+    del T, T2
+    packed, th, ph, Tt = _synth.half_grown(128, seed=1234)
+    st, df = _synth.unpack(packed)
+    t0 = time.perf_counter()
+    ev = kmc_event_rates.get_event_rates(st, th, ph, Tt, st, df, 128, 1, 2, 3, impurity_c=0.1)
+    dt = time.perf_counter() - t0
+    out["get_event_rates_128"] = {"value": 128 ** 3 / dt, "unit": "sites/s", "events": len(ev),
+                                  "what": "one call on the half-grown 128^3 lattice returning the reference's Python list of "
+                                          "tuples (building the list dominates); reference: 3.4e5 sites/s"}
+    return out
 
 
 def main():
@@ -165,9 +242,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cetkmc", choices=["cetkmc", "reference"])
-    ap.add_argument("--L", type=int, default=L_BENCH, help="sites per edge in a plane and planes per GPU")
+    ap.add_argument("--L", type=int, default=L_BENCH, help="edge length (strong) / sites per edge in a plane and planes per GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--thermal", default="cet", choices=["cet", "laser"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-api-e2e", action="store_true")
     ap.add_argument("--debug-flags", type=int, default=0, help="refresh variant for A/B runs (cet_debug_flags)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -178,11 +258,14 @@ def main():
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    if args.thermal == "laser" and world > 1:
+        raise SystemExit("--thermal laser is the single-GPU configuration (BASELINE configs[2])")
     warm = max(args.warmup, 3)
 
     import cetkmc
     from cetkmc import _synth
-    from cetkmc._config import rate_params, thermal_params
+    from cetkmc._config import rate_params, thermal_full_params, thermal_params
+    from cetkmc.kmc_simulation import slab_bounds
     cetkmc._lib.require_gpu()                       # no CPU fallback
     dist = None
     if world > 1:
@@ -192,11 +275,16 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     L = args.L
-    n0 = L * world
-    i_begin, i_end = rank * L, (rank + 1) * L
+    if args.scaling == "weak":
+        n0 = L * world
+        i_begin, i_end = rank * L, (rank + 1) * L
+    else:
+        n0 = L
+        i_begin, i_end = slab_bounds(L, world, rank)
     halo = 6 if world > 1 else 0
     packed, th, ph, T = _synth.half_grown(L, seed=1234, planes=(i_begin, i_end), n0=n0)
-    sites_local, sites_total = L ** 3, L ** 3 * world
+    own_planes = i_end - i_begin
+    sites_total = n0 * L * L
 
     ctx = cetkmc.Context(L=L, n0=n0, device=local_rank, i_begin=i_begin, i_end=i_end, halo=halo)
     ctx.debug_flags(args.debug_flags)
@@ -213,21 +301,52 @@ def main():
         ctx.halo_exchange(7)
     sp = cetkmc._lib.SweepParams()
     sp.seed, sp.events_per_sweep, sp.p_max = 42, EVENTS_FRACTION * sites_total, P_MAX
-    sp.defect_fraction, sp.thermal_every = 3e-3, THERMAL_EVERY
-    tp = thermal_params(1e-6, nan_to_num=True)
+    sp.defect_fraction = 3e-3
+    laser = args.thermal == "laser"
+    sp.thermal_every = 0 if laser else THERMAL_EVERY
+    tp = None if laser else thermal_params(1e-6, nan_to_num=True)
+    if laser:
+        from cetkmc.thermal_solver import DEFAULT_ABSORPTIVITY, DEFAULT_BEAM_RADIUS, laser_source_top
+        tfp = thermal_full_params(1e-6)
+        pool = {"j": 0.25 * L}
+        ctx.snapshot_state()
+
+        def laser_step():
+            # thermal_solver.update_temperature (:36-105) on the resident lattice: the top-plane source (L^2 values,
+            # formed on the host with the reference's expression) follows the melt pool along axis 1
+            ctx.thermal_full(tfp, laser_source_top(L, (0.0, pool["j"]), 200.0, DEFAULT_BEAM_RADIUS, DEFAULT_ABSORPTIVITY))
+            ctx.snapshot_state()
+            pool["j"] += 4.0
+
+    def run_block(n):
+        """n sweeps; with the laser the thermal step is driven from here before every 20-sweep block."""
+        tot = None
+        done = 0
+        while done < n:
+            blk = min(n - done, THERMAL_EVERY) if laser else n - done
+            if laser:
+                laser_step()
+            r = ctx.sweep_run(blk, sp, tp)
+            if tot is None:
+                tot = dict(r)
+            else:
+                for k in ("events_applied", "events_fired", "sites_refreshed", "sweeps_done"):
+                    tot[k] += r[k]
+            done += blk
+        return tot
 
     def barrier():
         ctx.sync()
         if dist is not None:
             dist.barrier()
 
-    ctx.sweep_run(warm, sp, tp)                     # warm-up (sweep 0 only measures the total rate)
+    run_block(warm)                                 # warm-up (a fresh clock is primed inside the first call)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     ctx.profile_enable(True)
     ctx.timer_begin()
-    res = ctx.sweep_run(args.steps, sp, tp)
+    res = run_block(args.steps)
     ms = ctx.timer_end_ms()
     clocks = sampler.stop()
     ctx.profile_enable(False)
@@ -247,77 +366,70 @@ def main():
     value = sites_total * args.steps / (ms * 1e-3)
     peak, peak_kind = peaks()
     # planes a dense kernel processes: the owned planes plus the ghost planes it must evaluate (N > 1)
-    eval_planes = (i_end - i_begin) + (0 if world == 1 else (4 if rank in (0, world - 1) else 8))
-    eval_sites = eval_planes * L * L
+    ghost_eval = 0 if world == 1 else (4 if rank in (0, world - 1) else 8)
+    eval_sites = (own_planes + ghost_eval) * L * L
 
-    def roof(kind, nbytes):
+    def roof(kind, nbytes, layout_bytes=None):
         t_ms, n = prof[kind]
         if n == 0 or t_ms <= 0:
             return None
         ach = nbytes / (t_ms / n * 1e-3) / 1e9
-        return {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "launches": int(n),
-                "ms_per_launch": t_ms / n, "bytes_per_launch": nbytes}
-
-    def roof_rates():
-        # full rebuilds (one per thermal step) plus, for N > 1, the 6-plane ghost-zone rebuilds of every sweep
-        t_ms, n = prof["rates"]
-        n_full = prof["thermal"][1]
-        if n == 0 or t_ms <= 0:
-            return None
-        faces = 0 if world == 1 else (1 if rank in (0, world - 1) else 2)
-        nbytes = BYTES_RATES * (n_full * eval_sites + args.steps * faces * 6 * L * L)
-        ach = nbytes / (t_ms * 1e-3) / 1e9
-        return {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "launches": int(n),
-                "ms_total": t_ms, "bytes_total": nbytes}
+        r = {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "launches": int(n),
+             "ms_per_launch": t_ms / n, "bytes_per_launch": nbytes}
+        if layout_bytes is not None:
+            r["bytes_layout_per_launch"] = layout_bytes
+            r["frac_layout"] = layout_bytes / (t_ms / n * 1e-3) / 1e9 / peak
+        return r
 
     refreshed = res["sites_refreshed"] / max(args.steps, 1)
     rl = {
         "sweep_stream_kernel": roof("decide", BYTES_STREAM * eval_sites),
-        "dirty_scan+dirty_eval (neighbour-rate refresh)": roof("refresh", BYTES_RATES * refreshed + BYTES_STAMP * eval_sites),
-        "rates_tile_kernel (dense rebuild after the thermal step)": roof_rates(),
-        "thermal_kernel": roof("thermal", BYTES_THERMAL * (i_end - i_begin) * L * L),
+        "dirty_scan + dirty_eval_compact (neighbour-rate refresh)":
+            roof("refresh", BYTES_RATES * refreshed + BYTES_STAMP * eval_sites, BYTES_RATES_LAYOUT * refreshed + BYTES_STAMP * eval_sites),
+        "rates_compact_kernel (dense rebuild after the thermal step)":
+            roof("rates", BYTES_RATES * eval_sites, BYTES_RATES_LAYOUT * eval_sites),
+        "thermal_kernel": roof("thermal", BYTES_THERMAL * own_planes * L * L),
     }
-    share = {k: prof[k][0] for k in ("decide", "pick", "apply", "refresh", "thermal", "rates", "halo", "allreduce")}
-    share["boundary_other"] = max(prof["boundary"][0] - (prof["rates"][0] - 0.0 if world > 1 else 0.0), 0.0) if world > 1 else 0.0
+    share = {k: prof[k][0] for k in ("decide", "pick", "apply", "refresh", "thermal", "rates", "halo", "allreduce", "boundary")}
     dominant = max(share, key=share.get)
-    dom_name = {"decide": "sweep_stream_kernel", "refresh": "dirty_scan+dirty_eval (neighbour-rate refresh)",
-                "rates": "rates_tile_kernel (dense rebuild after the thermal step)", "thermal": "thermal_kernel"}.get(dominant)
-    traffic = None                   # dram__bytes_read+write per launch from the committed ncu capture
+    dom_name = {"decide": "sweep_stream_kernel", "refresh": "dirty_scan + dirty_eval_compact (neighbour-rate refresh)",
+                "rates": "rates_compact_kernel (dense rebuild after the thermal step)", "thermal": "thermal_kernel"}.get(dominant)
+    traffic = None                   # dram__bytes_read+write per launch of the dominant kernel, from this round's ncu capture
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             per = json.load(f)["per_kernel"]
-        pick_k = {"decide": ["sweep_stream_kernel"], "refresh": ["dirty_scan_kernel", "dirty_eval_kernel"],
-                  "rates": ["rates_tile_kernel"], "thermal": ["thermal_kernel_v2"]}.get(dominant, [])
-        vals = [v for k, v in per.items() if any(n in k for n in pick_k)]
-        traffic = sum(vals[:len(pick_k)]) if vals else None
+        pick_k = {"decide": ["sweep_stream_kernel"], "refresh": ["dirty_scan_kernel", "dirty_eval_compact_kernel"],
+                  "rates": ["rates_compact_kernel"], "thermal": ["thermal_kernel_v2"]}.get(dominant, [])
+        vals = [v for n in pick_k for k, v in per.items() if n in k]
+        traffic = sum(vals) if len(vals) == len(pick_k) and vals else None
     except Exception:
         pass
     main_roof = dict(rl[dom_name]) if dom_name and rl.get(dom_name) else {"achieved": None, "peak": peak, "unit": "GB/s", "frac": None}
     main_roof.update({"bound": "hbm", "kernel": dom_name or dominant, "traffic": traffic, "peak_kind": peak_kind,
                       "share_of_step": share[dominant] / max(sum(share.values()), 1e-9)})
-    n_rates = prof["rates"][1]
+    n_thermal = int(prof["thermal"][1])
     out = {
         "metric": "kmc_site_updates_per_s", "value": value, "unit": "site-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"half-grown lattice {n0}x{L}x{L} (SURVEY 8d-ii: 25% solid, salt-and-pepper below a "
-                               f"wavy front, linear G), {L} planes per GPU, synchronous-sublattice sweeps with resident "
-                               f"rates + neighbour-rate refresh, thermal stencil and dense rate rebuild every "
-                               f"{THERMAL_EVERY} sweeps, events_per_sweep={EVENTS_FRACTION}N, p_max={P_MAX}",
-                   "l2": "fields swept per step (>= 1 GB rate sums per sweep) exceed the 126 MB L2; no flush needed",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args, world),
+                   "l2": "fields swept per step (>= 1 GB rate sums per sweep at 512^3) exceed the 126 MB L2; no flush needed",
+                   "thermal_in_window": f"{n_thermal} thermal step(s) + dense rebuild(s) fall inside the {args.steps} timed sweeps "
+                                        f"(cadence {THERMAL_EVERY})",
                    "parallelism": f"zslab{world}"},
         "executed_events_per_s": events / (ms * 1e-3),
         "kernel_ms_per_step": {k: v / args.steps for k, v in share.items()},
         "step_span_ms": prof["step"][0] / args.steps,
         "roofline": main_roof,
         "roofline_all": rl,
-        # per sweep: reset, stream, plane-reduce, pick, apply, dirty-scan, dirty-eval, finalize
-        "gpu_launches": int(8 * args.steps + prof["thermal"][1] + n_rates),
+        # per sweep: reset, stream, plane-reduce, pick, apply, stamp scan, refresh, finalize; per thermal step: stencil,
+        # pair-operand update, dense rebuild; N > 1 adds 2 tile-state kernels + 2 stamp fills per cut face
+        "gpu_launches": int(8 * args.steps + 3 * n_thermal + (0 if world == 1 else 4 * args.steps)),
         "clocks": clocks,
     }
 
-    # ---- e2e: the public API call with host buffers (copies inside the timed region) -----------
-    if not args.no_e2e:
+    # ---- e2e: the sweep API call with host buffers (copies inside the timed region) ------------
+    if not args.no_e2e and not laser:
         from cetkmc.kmc_simulation import run_kmc_sublattice_slab
         hp, _k1 = pinned(packed.shape, np.uint8); hp[...] = packed
         hth, _k2 = pinned(th.shape, np.float64); hth[...] = th
@@ -343,11 +455,15 @@ def main():
         d2h = r["packed"].nbytes + r["theta"].nbytes + r["phi"].nbytes
         out["e2e"] = {"value": sites_total * args.steps / dt, "unit": "site-updates/s",
                       "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
-                      "what": f"upload packed state+theta+phi+T from pinned host memory, {args.steps} sweeps, "
-                              "download packed state+theta+phi into pinned host memory; one call"}
+                      "what": f"run_kmc_sublattice_slab: upload packed state+theta+phi+T from pinned host memory, {args.steps} "
+                              "sweeps, download packed state+theta+phi into pinned host memory; one call.  The sweep has no "
+                              "reference-signature counterpart; the reference-signature calls are timed under api_e2e"}
         del res_keep
     ctx.close()
+    del packed, th, ph, T
 
+    if rank == 0 and world == 1 and not args.no_api_e2e and not laser:
+        out["api_e2e"] = api_e2e()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, dt, reps = cpu_rate_sample(threads)

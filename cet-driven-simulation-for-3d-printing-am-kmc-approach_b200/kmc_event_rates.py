@@ -79,9 +79,9 @@ def _tuples(ev, L):
     ti = np.where(has, tgt // LL, -1).tolist()
     tj = np.where(has, (tgt // L) % L, -1).tolist()
     tk = np.where(has, tgt % L, -1).tolist()
-    names = [_lib.EV_NAMES[t] for t in ev["type"].tolist()]
-    return [(n, (a, b, c), r, (d, e, f), at) for n, a, b, c, r, d, e, f, at in
-            zip(names, pi, pj, pk, ev["rate"].tolist(), ti, tj, tk, ev["atom"].tolist())]
+    names = np.array(_lib.EV_NAMES, dtype=object)[ev["type"]].tolist()
+    # nested zips build the position / target tuples in C: the list of ~3 events per site dominates the call
+    return list(zip(names, zip(pi, pj, pk), ev["rate"].tolist(), zip(ti, tj, tk), ev["atom"].tolist()))
 
 
 def get_event_rates(state, orientation_theta, orientation_phi, T, atom_type, defects_mask, L,
