@@ -269,6 +269,8 @@ def main():
     cetkmc._lib.require_gpu()                       # no CPU fallback
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner out of the one-JSON-line stdout
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)

@@ -109,6 +109,47 @@ int comm_halo_exchange(cet_ctx *c, int fields)
     return 0;
 }
 
+int comm_delta_alloc(cet_ctx *c)
+{
+    if (c->delta_cap) return 0;
+    // 1/16 of the zone sites: a sweep changes well under 1 % of them inside the validated envelope
+    c->delta_cap = (int64_t)DELTA_ZONE * c->plane / 16 + 1024;
+    const size_t bytes = DELTA_HEADER + (size_t)c->delta_cap * sizeof(DeltaEntry);
+    for (int f = 0; f < 2; ++f) {
+        CET_CUDA(cudaMalloc(&c->delta_send[f], bytes));
+        CET_CUDA(cudaMalloc(&c->delta_recv[f], bytes));
+        CET_CUDA(cudaMemsetAsync(c->delta_send[f], 0, bytes, c->stream));
+        CET_CUDA(cudaMemsetAsync(c->delta_recv[f], 0, bytes, c->stream));
+    }
+    return 0;
+}
+
+// One message per neighbour and direction: header + the full entry capacity (the two sides of an
+// NCCL send/recv must agree on the size, and a count round trip would cost another latency).
+int comm_delta_exchange(cet_ctx *c)
+{
+    if (c->world <= 1) return 0;
+    CET_REQUIRE(c->nccl_comm != nullptr && c->delta_cap > 0, "delta exchange: communicator / buffers missing");
+    ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+    const size_t bytes = DELTA_HEADER + (size_t)c->delta_cap * sizeof(DeltaEntry);
+    const int lower = c->rank - 1, upper = c->rank + 1;
+    CET_NCCL(g_nccl.GroupStart());
+    ncclResult_t first = ncclSuccess;
+    auto op = [&](ncclResult_t r) { if (first == ncclSuccess) first = r; };
+    if (lower >= 0) {
+        op(g_nccl.Send(c->delta_send[0], bytes, ncclChar, lower, comm, c->stream));
+        op(g_nccl.Recv(c->delta_recv[0], bytes, ncclChar, lower, comm, c->stream));
+    }
+    if (upper < c->world) {
+        op(g_nccl.Send(c->delta_send[1], bytes, ncclChar, upper, comm, c->stream));
+        op(g_nccl.Recv(c->delta_recv[1], bytes, ncclChar, upper, comm, c->stream));
+    }
+    const ncclResult_t end = g_nccl.GroupEnd();
+    CET_NCCL(first);
+    CET_NCCL(end);
+    return 0;
+}
+
 // plane_sum[0..n) holds this slab's plane totals (zeros elsewhere, all >= 0) and max_inout the
 // local maximum, stored contiguously at plane_sum[n].  Every entry is non-zero on at most one
 // rank, so ONE max-all-reduce over n+1 doubles yields both the gathered plane sums (bit-exact,

@@ -37,6 +37,15 @@ struct KmcState {
     int32_t terminated, starved;
 };
 
+// One changed boundary-zone site of a sweep, as its owner sends it to the neighbouring slab.
+struct DeltaEntry {
+    double theta, phi;
+    int32_t zidx;        // (plane within the 6-plane zone) * plane_sites + in-plane index
+    uint32_t vox;        // the packed voxel byte
+};
+constexpr int DELTA_ZONE = 6;      // planes per face a neighbour keeps as ghosts (= SWEEP_HALO)
+constexpr int DELTA_HEADER = 16;   // bytes in front of the entries; the first 4 hold the count
+
 struct SweepState {
     unsigned long long n_fired_total, n_applied, n_nuc;   // running totals over owned sites (device atomics)
     unsigned long long n_refreshed_total;                 // sites re-evaluated by the neighbour-rate refresh
@@ -148,6 +157,10 @@ struct cet_ctx {
     // NCCL
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
+    // delta halo exchange of the sweeps (comm.cu): per cut face one send and one receive buffer,
+    // [0] lower face, [1] upper face; layout: 16-byte header (entry count) + DeltaEntry[delta_cap]
+    void *delta_send[2] = {nullptr, nullptr}, *delta_recv[2] = {nullptr, nullptr};
+    int64_t delta_cap = 0;
 
     cet::Lat lat() const
     {

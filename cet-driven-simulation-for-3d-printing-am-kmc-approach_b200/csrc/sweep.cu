@@ -43,6 +43,8 @@ int rates_rows(cet_ctx *c, int p_lo, int p_hi);                                 
 int rates_rows_dirty(cet_ctx *c, int p_lo, int p_hi, const uint32_t *stamp, int32_t *list, unsigned int *counter);
 int comm_sweep_reduce(cet_ctx *c, double *plane_sum, int n, double *max_inout);   // comm.cu
 int comm_halo_exchange(cet_ctx *c, int fields);
+int comm_delta_alloc(cet_ctx *c);
+int comm_delta_exchange(cet_ctx *c);
 // sweep_tile.cu — the fused tile kernel (refresh + stream) and the arrays it stages
 int tile_state_ensure(cet_ctx *c);
 int tile_state_build(cet_ctx *c, int p_lo, int p_hi);
@@ -346,7 +348,31 @@ struct ApplyArgs {
     double *pairop;
     const double *T;
     uint64_t tlut;
+    // delta halo exchange: owned sites changed within DELTA_ZONE planes of a cut face are appended to the
+    // face's send buffer (NULL: no neighbour on that side)
+    unsigned char *delta_lo, *delta_hi;
+    unsigned int delta_cap;
 };
+
+// the owner of `site` tells the neighbouring slab(s) what the site holds now
+__device__ __forceinline__ void delta_emit(const ApplyArgs &a, int site)
+{
+    const int LL = a.L * a.L;
+    const int p = site / LL;
+    if (p < a.own_lo || p >= a.own_hi) return;
+#pragma unroll
+    for (int face = 0; face < 2; ++face) {
+        unsigned char *buf = face == 0 ? a.delta_lo : a.delta_hi;
+        const int z0 = face == 0 ? a.own_lo : a.own_hi - DELTA_ZONE;
+        if (!buf || p < z0 || p >= z0 + DELTA_ZONE) continue;
+        const unsigned int q = atomicAdd(reinterpret_cast<unsigned int *>(buf), 1u);
+        if (q >= a.delta_cap) { a.ss->overflow = 1; continue; }
+        DeltaEntry e;
+        e.theta = a.theta[site]; e.phi = a.phi[site];
+        e.zidx = site - z0 * LL; e.vox = a.vox[site];
+        reinterpret_cast<DeltaEntry *>(buf + DELTA_HEADER)[q] = e;
+    }
+}
 
 // cvox / pairop of a site that now holds `state` with orientation z component z
 __device__ __forceinline__ void tile_put(const ApplyArgs &a, int site, int state, double z)
@@ -441,8 +467,11 @@ __global__ void __launch_bounds__(128) sweep_apply_kernel(const __grid_constant_
             if (ety == CET_EV_DIFF) {
                 site_changed(a, s, src_state, 0);
                 site_changed(a, tgt, 0, upd_state);
+                delta_emit(a, s);
+                delta_emit(a, tgt);
             } else {
                 site_changed(a, s, 0, upd_state);
+                delta_emit(a, s);
             }
         }
         // release the claims this event holds (only the top claimant of a site clears it)
@@ -454,6 +483,27 @@ __global__ void __launch_bounds__(128) sweep_apply_kernel(const __grid_constant_
         if (fired) atomicAdd(&a.ss->n_fired_total, (unsigned long long)fired);
         if (applied) atomicAdd(&a.ss->n_applied, (unsigned long long)applied);
         if (nuc) atomicAdd(&a.ss->n_nuc, (unsigned long long)nuc);
+    }
+}
+
+// Receiver side of the delta exchange: the neighbour's changed sites are written into the ghost planes
+// [g0, g0 + DELTA_ZONE) — lattice, orientation vector, tile state — and stamped (with their neighbours)
+// for the refresh pass.
+__global__ void __launch_bounds__(128) delta_scatter_kernel(const __grid_constant__ ApplyArgs a, const unsigned char *buf, int g0)
+{
+    const unsigned int n = min(*reinterpret_cast<const unsigned int *>(buf), a.delta_cap);
+    const DeltaEntry *ent = reinterpret_cast<const DeltaEntry *>(buf + DELTA_HEADER);
+    const int LL = a.L * a.L;
+    for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const DeltaEntry e = ent[q];
+        const int site = g0 * LL + e.zidx;
+        const int old_state = a.vox[site] & 0x0F, new_state = (int)(e.vox & 0x0Fu);
+        a.vox[site] = (uint8_t)e.vox;
+        a.theta[site] = e.theta; a.phi[site] = e.phi;
+        const Vec4 uv = unit_vec4(e.theta, e.phi);
+        a.v[site] = uv;
+        tile_put(a, site, new_state, uv.z);
+        site_changed(a, site, old_state, new_state);
     }
 }
 
@@ -628,6 +678,7 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
         c->plane_sum, max_slot);
     CET_CUDA(cudaGetLastError());
     const int sparse_grid = sm_count(c) * 32;
+    ApplyArgs apply_args;
     {
         PickArgs a;
         a.g = c->lat(); a.theta = c->theta; a.phi = c->phi; a.site_rate = c->site_rate; a.dep_rate = c->dep_rate;
@@ -648,6 +699,13 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
         b.seed = sp->seed; b.sweep = (uint32_t)c->sweep_index;
         b.defect_fraction = sp->defect_fraction;
         b.cvox = tiled ? c->cvox : nullptr; b.pairop = c->pairop; b.T = c->T; b.tlut = tile_code_lut(c->rp);
+        const bool deltas = tiled && c->world > 1 && count;
+        b.delta_lo = (deltas && c->rank > 0) ? (unsigned char *)c->delta_send[0] : nullptr;
+        b.delta_hi = (deltas && c->rank < c->world - 1) ? (unsigned char *)c->delta_send[1] : nullptr;
+        b.delta_cap = (unsigned int)c->delta_cap;
+        if (b.delta_lo) CET_CUDA(cudaMemsetAsync(b.delta_lo, 0, DELTA_HEADER, c->stream));
+        if (b.delta_hi) CET_CUDA(cudaMemsetAsync(b.delta_hi, 0, DELTA_HEADER, c->stream));
+        apply_args = b;
         ProfScope ps(c, PROF_APPLY);
         sweep_apply_kernel<<<sparse_grid, 128, 0, c->stream>>>(b);
     }
@@ -668,27 +726,40 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
     sweep_finalize_kernel<<<1, 256, 0, c->stream>>>(c->sweep, c->plane_sum, (int)c->n0, max_slot,
                                                     sp->events_per_sweep, sp->p_max);
     CET_CUDA(cudaGetLastError());
-    if (c->world > 1) {
-        {
-            ProfScope ps(c, PROF_HALO);
-            if (int rc = comm_halo_exchange(c, 1 | 2)) return rc;
-        }
-        // The ghost planes now hold the owners' lattice.  Events this slab could not resolve
-        // (write set reaching beyond ghost depth 2) may have changed ghost planes that the two
-        // outermost owned planes read, so the evaluated ghost planes and those two owned planes on
-        // each cut face are re-evaluated: densely (gather path), or by stamping them into the one
-        // refresh pass of the sweep (tile path).
+    if (c->world > 1 && count) {
         if (tiled) {
+            // Delta exchange: every slab sends the owned sites it changed within DELTA_ZONE planes of a cut
+            // face (one fixed-capacity message per neighbour, ~24 B per site) and writes what it receives
+            // into its ghost planes, stamping those sites and their neighbours; the one refresh pass of the
+            // sweep then covers the slab's own events and the ghost updates alike.  Ghost planes 4-5 were
+            // already updated by the locally resolved events with the owner's outcome (same inputs, same
+            // deterministic claims), planes 0-3 only by the deltas.
+            {
+                ProfScope ps(c, PROF_HALO);
+                if (int rc = comm_delta_exchange(c)) return rc;
+            }
             {
                 ProfScope pb(c, PROF_BOUNDARY);
-                if (int rc = tile_state_build(c, 0, R.own_lo)) return rc;
-                if (int rc = tile_state_build(c, R.own_hi, (int)c->np)) return rc;
-                if (R.own_lo > R.eval_lo) if (int rc = stamp_fill(c, R.eval_lo, R.own_lo + 2)) return rc;
-                if (R.eval_hi > R.own_hi) if (int rc = stamp_fill(c, R.own_hi - 2, R.eval_hi)) return rc;
+                ApplyArgs d = apply_args;
+                d.delta_lo = d.delta_hi = nullptr;
+                if (c->rank > 0)
+                    delta_scatter_kernel<<<sm_count(c) * 4, 128, 0, c->stream>>>(d, (const unsigned char *)c->delta_recv[0], 0);
+                if (c->rank < c->world - 1)
+                    delta_scatter_kernel<<<sm_count(c) * 4, 128, 0, c->stream>>>(d, (const unsigned char *)c->delta_recv[1],
+                                                                                 (int)c->np - DELTA_ZONE);
+                CET_CUDA(cudaGetLastError());
             }
             ProfScope ps(c, PROF_REFRESH);
             if (int rc = refresh_tiled(c, R)) return rc;
         } else {
+            {
+                ProfScope ps(c, PROF_HALO);
+                if (int rc = comm_halo_exchange(c, 1 | 2)) return rc;
+            }
+            // The ghost planes now hold the owners' lattice.  Events this slab could not resolve
+            // (write set reaching beyond ghost depth 2) may have changed ghost planes that the two
+            // outermost owned planes read, so the evaluated ghost planes and those two owned planes on
+            // each cut face are rebuilt densely.
             ProfScope pb(c, PROF_BOUNDARY);
             c->nst_valid = true;       // the exchange marked the whole cache stale; only the planes rebuilt below are
             if (R.own_lo > R.eval_lo) {
@@ -742,6 +813,7 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
     }
     if (tiled) {
         c->nst_valid = false;                // the tile path keeps no neighbour cache
+        if (c->world > 1) if (int rc = comm_delta_alloc(c)) return rc;
     } else {
         c->tile_valid = false;               // the gather path's apply does not maintain cvox / pairop
         if (int rc = nst_ensure(c)) return rc;
