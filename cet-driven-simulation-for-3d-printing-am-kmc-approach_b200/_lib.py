@@ -112,6 +112,7 @@ SIGNATURES = {
     "cet_grains_label_ex": [_VP, _F64, C.c_int, C.POINTER(_I64)],
     "cet_grains_stats": [_VP, _I64, _VP, _VP, _VP, _VP],
     "cet_grains_download_labels": [_VP, _VP],
+    "cet_grains_download_planes": [_VP, _I64, _I64, _VP],
     "cet_debug_nst_mismatches": [_VP, C.POINTER(_I64)],
     "cet_debug_flags": [_VP, C.c_int],
     "cet_profile_enable": [_VP, C.c_int],
@@ -209,6 +210,8 @@ class Context:
             self.shape = (n0, L, L)
             self.i_begin, self.i_end, self.halo = int(i_begin), i_end, int(halo)
         self.device = device
+        self.n0 = self.shape[0]
+        self.rank, self.world = 0, 1
         self.owned_shape = (self.i_end - self.i_begin, self.shape[1], self.shape[2])
 
     # -- life cycle -------------------------------------------------------------------------
@@ -379,6 +382,7 @@ class Context:
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         buf = C.create_string_buffer(bytes(unique_id), 128)
         check(lib().cet_comm_init(self._h, buf, rank, world), "cet_comm_init")
+        self.rank, self.world = int(rank), int(world)
 
     def halo_exchange(self, fields=7):
         check(lib().cet_halo_exchange(self._h, int(fields)), "cet_halo_exchange")
@@ -427,6 +431,27 @@ class Context:
             occ = lab >= 0
             vis[occ] = np.searchsorted(out["root"], lab[occ]).astype(np.int32) + 1
             out["labels"] = vis
+        return out
+
+    def grains_local(self, theta_threshold=0.5):
+        """Slab-local labelling (owned planes + 2 ghost planes per cut face; the ghost planes must be
+        current): dict of root (GLOBAL site index of each local component's first voxel), size (owned
+        voxels), box_lo / box_hi (global coordinates), unsorted.  metrics.grains_distributed joins the
+        components of all slabs."""
+        n = C.c_int64(0)
+        check(lib().cet_grains_label_ex(self._h, float(theta_threshold), 0, C.byref(n)), "cet_grains_label_ex")
+        n = n.value
+        root, size = np.empty(n, np.int32), np.empty(n, np.int32)
+        lo, hi = np.empty((n, 3), np.int32), np.empty((n, 3), np.int32)
+        if n:
+            check(lib().cet_grains_stats(self._h, n, _ptr(root), _ptr(size), _ptr(lo), _ptr(hi)), "cet_grains_stats")
+        return dict(root=root.astype(np.int64), size=size.astype(np.int64), box_lo=lo, box_hi=hi)
+
+    def grain_label_planes(self, i_lo, i_hi):
+        """Labels (global root index, -1 = empty) of global planes [i_lo, i_hi) of the last labelling."""
+        n1, n2 = self.owned_shape[1], self.owned_shape[2]
+        out = np.empty((int(i_hi - i_lo), n1, n2), np.int32)
+        check(lib().cet_grains_download_planes(self._h, int(i_lo), int(i_hi), _ptr(out)), "cet_grains_download_planes")
         return out
 
     def nst_mismatches(self):

@@ -90,10 +90,32 @@ def _gr(L, temp, nu_dep):
     return G, R, R_phys, (G / R_phys if R_phys > 0 else np.inf)
 
 
+def _slab_comm(world):
+    """Rendezvous helpers of a multi-GPU run (one process per GPU under torch.distributed.run): the
+    process group is only plumbing — NCCL unique id broadcast and the small host-side gathers of the
+    metrics cadence; the lattice exchange itself is libcetkmc's (comm.cu)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+
+    def all_gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    def bcast_bytes(b):
+        box = [b]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+    return all_gather, bcast_bytes
+
+
 def run_cet_sublattice(L=None, n_sweeps=2000, temp=None, defect_fraction=0.0, n_seeds=5, impurity_c=0.0,
                        output_prefix="cet_sublattice", metrics_every=None, events_per_sweep=None, p_max=0.1,
                        nu_dep=None, laser=None, thermal_every=_ks.THERMAL_EVERY, device=0, seed=None,
-                       checkpoint_every=0, resume_from=None, lattice=None, verbose=True):
+                       checkpoint_every=0, resume_from=None, lattice=None, verbose=True, rank=0, world=1,
+                       mask_stream="numpy"):
     """run_kmc's large-lattice sibling.  Same set-up (initialize_lattice + introduce_defects with the
     run's seed), same cadence and CSV; the steps are synchronous-sublattice sweeps (csrc/sweep.cu), so
     `Step` counts sweeps and `Time` is the accumulated sweep interval.
@@ -103,6 +125,17 @@ def run_cet_sublattice(L=None, n_sweeps=2000, temp=None, defect_fraction=0.0, n_
            beam_radius=m, absorptivity=) -> thermal_solver.update_temperature with the moving source.
     lattice: optional (state, theta, phi, T, atom_type[, defects]) to start from instead of
            initialize_lattice.  Returns (state, atom_type, total_time, theta, phi) like run_kmc.
+    world > 1: the lattice is split into z-slabs, one per rank / GPU (launch every rank with the same
+           arguments plus its rank; torch.distributed.run provides the rendezvous).  The trajectory and
+           the CSV do not depend on the number of slabs.  Rank 0 writes the CSV; every rank returns its
+           own planes.  The laser variant and checkpoints are single-GPU.
+    mask_stream: "numpy" — the 200-step defect-mask refresh consumes NumPy's global stream in C order
+           like defects.py:18 (single GPU only); "philox" — the device's counter-based stream keyed by
+           (seed, refresh number, global site), which a slab run always uses (an ordered host stream
+           cannot be split over slabs); a single-GPU run with "philox" equals the slab run bit for bit.
+    `Time` is the accumulated sweep interval (a physical clock); run_kmc's CSV carries the reference's
+    clock, which its 1e-12 s floor makes a step counter (Time = 1e-12 s x steps) — the two
+    columns are not comparable and level-3 parity is therefore matched by executed events (tests).
     """
     L = constants.LATTICE_SIZE if L is None else int(L)
     temp = constants.T_SUB if temp is None else temp
@@ -114,7 +147,14 @@ def run_cet_sublattice(L=None, n_sweeps=2000, temp=None, defect_fraction=0.0, n_
     os.makedirs(output_dir, exist_ok=True)
     consts = _gr(L, temp, nu_dep)
 
-    ctx = _lib.Context(L=L, device=device)
+    if world > 1 and (laser or checkpoint_every or resume_from):
+        raise ValueError("run_cet_sublattice: the laser variant and checkpoint / resume are single-GPU")
+    if mask_stream not in ("numpy", "philox"):
+        raise ValueError("mask_stream must be 'numpy' or 'philox'")
+    philox_mask = world > 1 or mask_stream == "philox"
+    all_gather = None
+    i_begin, i_end = _ks.slab_bounds(L, world, rank)
+    ctx = _lib.Context(L=L, device=device, i_begin=i_begin, i_end=i_end, halo=_ks.SWEEP_HALO if world > 1 else 0)
     try:
         ctx.set_rate_params(rate_params(impurity_c, 1, 2, 3, overrides={"NU_DEP": nu_dep}))
         sweep0, total_time, nucleation_count, cet_detected, rows = 0, 0.0, 0, False, []
@@ -131,7 +171,13 @@ def run_cet_sublattice(L=None, n_sweeps=2000, temp=None, defect_fraction=0.0, n_
             else:
                 state, theta, phi, T, atom_type = lattice[:5]
                 defects_mask = lattice[5] if len(lattice) > 5 else None
-            ctx.upload(state=np.ascontiguousarray(state, dtype=np.int64), theta=theta, phi=phi, T=T, defects=defects_mask)
+            own = slice(i_begin, i_end)
+            ctx.upload(state=np.ascontiguousarray(state[own], dtype=np.int64), theta=theta[own], phi=phi[own], T=T[own],
+                       defects=None if defects_mask is None else defects_mask[own])
+        if world > 1:
+            all_gather, bcast_bytes = _slab_comm(world)
+            ctx.comm_init(bcast_bytes(_lib.comm_unique_id() if rank == 0 else None), rank, world)
+            ctx.halo_exchange(7)
         sp = _lib.SweepParams()
         sp.seed = seed
         sp.events_per_sweep = float(events_per_sweep if events_per_sweep is not None else 0.005 * L ** 3)
@@ -157,7 +203,7 @@ def run_cet_sublattice(L=None, n_sweeps=2000, temp=None, defect_fraction=0.0, n_
                     l_pos[1] += float(laser.get("speed", 0.0))
                 res = ctx.sweep_run(blk, sp, tp)
                 total_time += res["time"]
-                nucleation_count += res["nucleation_count"]
+                nucleation_count += res["nucleation_count"] if world == 1 else int(np.sum(all_gather(res["nucleation_count"])))
                 done += res["sweeps_done"]
                 terminated = bool(res["terminated"]) or res["sweeps_done"] == 0
                 if res["overflow"]:
@@ -174,15 +220,23 @@ def run_cet_sublattice(L=None, n_sweeps=2000, temp=None, defect_fraction=0.0, n_
             sweep += done
             last = sweep - 1
             if last % every == 0:                                                     # kmc_simulation.py:335-338
-                _defects.refresh_resident(ctx)
+                if not philox_mask:
+                    _defects.refresh_resident(ctx)
+                else:
+                    ctx.defects_refresh(draws=None, seed=seed, epoch=last // every, prob_base=constants.DEFECT_PROB_BASE,
+                                        e_mig=_defects.E_MIGRATION, kT=constants.K_T, T_default=constants.T_SUB,
+                                        carbon_id=_defects.CARBON_ID, defect_id=constants.DEFECT_ID)
+                    if world > 1:
+                        ctx.halo_exchange(1)                                          # the ghost copies of the mask nibble
             row, cet_detected = _ks._metrics_row(last, total_time, nucleation_count, cet_detected, consts, ctx,
-                                                 verbose=verbose)
+                                                 verbose=verbose and rank == 0, all_gather=all_gather)
             rows.append(row)
             if checkpoint_every and (len(rows) % checkpoint_every == 0):
                 checkpoint(ctx, os.path.join(output_dir, "checkpoint"), sweep=sweep, time=total_time,
                            nucleation_count=nucleation_count, cet_detected=cet_detected,
                            rows=[{k: (v if not isinstance(v, (np.generic,)) else v.item()) for k, v in r.items()} for r in rows])
-        _ks._write_csv(rows, output_dir)
+        if rank == 0:
+            _ks._write_csv(rows, output_dir)
         f = ctx.download(state=True, atom_type=True, theta=True, phi=True)
     finally:
         ctx.close()

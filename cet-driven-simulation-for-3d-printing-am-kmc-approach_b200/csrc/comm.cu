@@ -112,8 +112,8 @@ int comm_halo_exchange(cet_ctx *c, int fields)
 int comm_delta_alloc(cet_ctx *c)
 {
     if (c->delta_cap) return 0;
-    // 1/16 of the zone sites: a sweep changes well under 1 % of them inside the validated envelope
-    c->delta_cap = (int64_t)DELTA_ZONE * c->plane / 16 + 1024;
+    // 1/32 of the zone sites (~19 % of a plane): at 0.5 % of the sites firing per sweep about 4 % of a plane change
+    c->delta_cap = (int64_t)DELTA_ZONE * c->plane / 32 + 1024;
     const size_t bytes = DELTA_HEADER + (size_t)c->delta_cap * sizeof(DeltaEntry);
     for (int f = 0; f < 2; ++f) {
         CET_CUDA(cudaMalloc(&c->delta_send[f], bytes));

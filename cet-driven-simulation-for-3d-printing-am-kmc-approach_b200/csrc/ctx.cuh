@@ -146,6 +146,7 @@ struct cet_ctx {
     // grain clustering (grains.cu)
     int *grain_label = nullptr, *grain_gid = nullptr;
     int64_t n_grains = 0;
+    int grain_p_lo = 0, grain_p_hi = 0;   // local planes the last labelling covered
 
     // per-kernel-kind device timing (cet_profile_*): event pairs recorded around the dominant
     // kernels on the context stream, resolved when the totals are read

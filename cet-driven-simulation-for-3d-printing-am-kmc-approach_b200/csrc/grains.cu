@@ -148,6 +148,7 @@ extern "C" {
 // utils.get_clusters (utils.py:69-84) on the resident lattice: label the grains of the owned
 // planes.  n_grains receives the number of components.
 int cet_grains_label_ex(cet_ctx *c, double theta_threshold, int criterion, int64_t *n_grains);
+int cet_grains_download_planes(cet_ctx *c, int64_t i_lo, int64_t i_hi, int32_t *labels);
 int cet_grains_label(cet_ctx *c, double theta_threshold, int64_t *n_grains)
 {
     return cet_grains_label_ex(c, theta_threshold, 0, n_grains);
@@ -159,19 +160,28 @@ int cet_grains_label_ex(cet_ctx *c, double theta_threshold, int criterion, int64
 {
     CET_REQUIRE(c && n_grains && c->cubic, "cet_grains_label: bad argument");
     CET_REQUIRE(criterion == 0 || criterion == 1, "cet_grains_label: unknown criterion %d", criterion);
-    CET_REQUIRE(c->nloc < (1ll << 31), "cet_grains_label: the local lattice must have fewer than 2^31 sites");
-    CET_REQUIRE(c->world == 1 && c->halo == 0, "cet_grains_label: grains are labelled on a whole lattice (one context)");
+    CET_REQUIRE(c->nloc < (1ll << 31) && c->n0 * c->plane < (1ll << 31),
+                "cet_grains_label: the lattice must have fewer than 2^31 sites");
+    CET_REQUIRE(c->halo == 0 || c->halo >= 2, "cet_grains_label: a slab needs at least 2 ghost planes");
     cet::DeviceGuard dg(c->device);
     if (!c->grain_label) CET_CUDA(cudaMalloc(&c->grain_label, (size_t)c->nloc * sizeof(int)));
     if (!c->grain_gid) CET_CUDA(cudaMalloc(&c->grain_gid, (size_t)c->nloc * sizeof(int)));
     if (int rc = ensure_stage(c, 64)) return rc;
     unsigned int *cnt = (unsigned int *)c->stage;
     CET_CUDA(cudaMemsetAsync(cnt, 0, 64, c->stream));
-    const int64_t lo = 0, hi = c->nloc;
-    const int grid = (int)std::min<int64_t>((hi + 255) / 256, (int64_t)sm_count(c) * 16);
+    // A slab labels its owned planes plus 2 ghost planes per cut face (the reach of the neighbourhood
+    // along axis 0): a grain that crosses the cut is then a local component on both sides, joined by
+    // the host through the labels both slabs give the shared planes (metrics.grains_distributed).
+    const int i_off = (int)(c->i_begin - c->halo);
+    int p_lo = c->halo >= 2 ? c->halo - 2 : 0, p_hi = (int)c->np - (c->halo >= 2 ? c->halo - 2 : 0);
+    if (i_off + p_lo < 0) p_lo = -i_off;
+    if (i_off + p_hi > c->n0) p_hi = (int)(c->n0 - i_off);
+    c->grain_p_lo = p_lo; c->grain_p_hi = p_hi;
+    const int64_t lo = (int64_t)p_lo * c->plane, hi = (int64_t)p_hi * c->plane;
+    const int grid = (int)std::min<int64_t>((hi - lo + 255) / 256, (int64_t)sm_count(c) * 16);
     grains_init_kernel<<<grid, 256, 0, c->stream>>>(c->vox, c->grain_label, lo, hi);
-    grains_union_kernel<<<grid, 256, 0, c->stream>>>(c->vox, c->v, criterion == 1 ? c->theta : nullptr, c->grain_label, (int)c->n1, 0,
-                                                     (int)c->np, criterion == 1 ? theta_threshold : cos(theta_threshold));
+    grains_union_kernel<<<grid, 256, 0, c->stream>>>(c->vox, c->v, criterion == 1 ? c->theta : nullptr, c->grain_label, (int)c->n1,
+                                                     p_lo, p_hi, criterion == 1 ? theta_threshold : cos(theta_threshold));
     grains_flatten_kernel<<<grid, 256, 0, c->stream>>>(c->grain_label, c->grain_gid, lo, hi, cnt);
     CET_CUDA(cudaGetLastError());
     unsigned int h = 0;
@@ -196,10 +206,14 @@ int cet_grains_stats(cet_ctx *c, int64_t cap, int32_t *root, int32_t *size, int3
     if (n == 0) return 0;
     GrainStat *st = nullptr;
     CET_CUDA(cudaMalloc(&st, (size_t)n * sizeof(GrainStat)));
-    const int64_t lo = 0, hi = c->nloc;
-    const int grid = (int)std::min<int64_t>((hi + 255) / 256, (int64_t)sm_count(c) * 16);
+    // roots anywhere in the labelled planes; voxels counted on the OWNED planes only, so that the
+    // statistics of a grain that spans several slabs add up (a local component without owned voxels
+    // reports size 0)
+    const int64_t lo = (int64_t)c->grain_p_lo * c->plane, hi = (int64_t)c->grain_p_hi * c->plane;
+    const int64_t o_lo = c->owned_offset(), o_hi = o_lo + c->owned_sites();
+    const int grid = (int)std::min<int64_t>((hi - lo + 255) / 256, (int64_t)sm_count(c) * 16);
     grains_stats_init_kernel<<<grid, 256, 0, c->stream>>>(c->grain_label, c->grain_gid, lo, hi, st);
-    grains_stats_kernel<<<grid, 256, 0, c->stream>>>(c->grain_label, c->grain_gid, lo, hi, st, (int)c->n1,
+    grains_stats_kernel<<<grid, 256, 0, c->stream>>>(c->grain_label, c->grain_gid, o_lo, o_hi, st, (int)c->n1,
                                                      (int)(c->i_begin - c->halo));
     std::vector<GrainStat> h(n);
     cudaError_t e = cudaGetLastError();
@@ -207,8 +221,9 @@ int cet_grains_stats(cet_ctx *c, int64_t cap, int32_t *root, int32_t *size, int3
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(st);
     if (e != cudaSuccess) { set_error("cet_grains_stats: %s", cudaGetErrorString(e)); return 1000 + (int)e; }
+    const int root_off = (int)((c->i_begin - c->halo) * c->plane);       // local -> global site index
     for (unsigned int g = 0; g < n; ++g) {
-        if (root) root[g] = h[g].root;
+        if (root) root[g] = h[g].root + root_off;
         if (size) size[g] = h[g].size;
         for (int ax = 0; ax < 3; ++ax) {
             if (box_lo) box_lo[3 * g + ax] = h[g].lo[ax];
@@ -222,11 +237,27 @@ int cet_grains_stats(cet_ctx *c, int64_t cap, int32_t *root, int32_t *size, int3
 // -1 for empty sites.  The reference's `visited` volume (utils.py:75-84) is rank-of-root + 1.
 int cet_grains_download_labels(cet_ctx *c, int32_t *labels)
 {
-    CET_REQUIRE(c && labels && c->grain_label, "cet_grains_download_labels: call cet_grains_label first");
+    CET_REQUIRE(c, "cet_grains_download_labels: NULL ctx");
+    return cet_grains_download_planes(c, c->i_begin, c->i_end, labels);
+}
+
+// Labels (GLOBAL site index of the local root, -1 for empty sites) of global planes [i_lo, i_hi), which
+// must lie within the planes the last cet_grains_label call labelled (owned + 2 ghost planes per cut face).
+int cet_grains_download_planes(cet_ctx *c, int64_t i_lo, int64_t i_hi, int32_t *labels)
+{
+    CET_REQUIRE(c && labels && c->grain_label, "cet_grains_download_planes: call cet_grains_label first");
+    const int64_t i_off = c->i_begin - c->halo;
+    CET_REQUIRE(i_lo < i_hi && i_lo - i_off >= c->grain_p_lo && i_hi - i_off <= c->grain_p_hi,
+                "cet_grains_download_planes: planes [%lld, %lld) were not labelled", (long long)i_lo, (long long)i_hi);
     cet::DeviceGuard dg(c->device);
-    CET_CUDA(cudaMemcpyAsync(labels, c->grain_label + c->owned_offset(), (size_t)c->owned_sites() * sizeof(int),
-                             cudaMemcpyDeviceToHost, c->stream));
+    const int64_t n = (i_hi - i_lo) * c->plane;
+    CET_CUDA(cudaMemcpyAsync(labels, c->grain_label + (i_lo - i_off) * c->plane, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost,
+                             c->stream));
     CET_CUDA(cudaStreamSynchronize(c->stream));
+    const int off = (int)(i_off * c->plane);
+    if (off)
+        for (int64_t q = 0; q < n; ++q)
+            if (labels[q] >= 0) labels[q] += off;
     return 0;
 }
 

@@ -57,12 +57,19 @@ def _replay(stream_state_setter, state, draw, n):
     draw(n)
 
 
-def _metrics_row(step, total_time, nucleation_count, cet_detected, consts, ctx, verbose=True):
-    """kmc_simulation.py:341-378 — one metrics.csv row, from the lattice resident in `ctx`."""
+def _metrics_row(step, total_time, nucleation_count, cet_detected, consts, ctx, verbose=True, all_gather=None):
+    """kmc_simulation.py:341-378 — one metrics.csv row, from the lattice resident in `ctx`; with
+    `all_gather` (a lattice split into z-slabs, one context per rank) from all slabs, identical on every rank."""
     G, R, R_phys, G_over_R_phys = consts
     counts = ctx.counts()
-    n_sites = int(np.prod(ctx.owned_shape))
-    m = _gpu_metrics.metrics_from_grains(ctx.grains(0.5), n_sites, voxel_size=constants.VOXEL_SIZE)
+    if all_gather is None:
+        n_sites = int(np.prod(ctx.owned_shape))
+        grains = ctx.grains(0.5)
+    else:
+        counts = np.sum(all_gather(counts), axis=0)
+        n_sites = int(ctx.n0 * ctx.owned_shape[1] * ctx.owned_shape[2])
+        grains = _gpu_metrics.grains_distributed(ctx, all_gather, 0.5)
+    m = _gpu_metrics.metrics_from_grains(grains, n_sites, voxel_size=constants.VOXEL_SIZE)
     n_w, n_re, n_c = int(counts[1]), int(counts[2]), int(counts[3])
     defect_voxels = int(counts[constants.DEFECT_ID])
     m["Defect_voxel_count"] = defect_voxels

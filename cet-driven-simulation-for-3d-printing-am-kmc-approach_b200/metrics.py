@@ -82,6 +82,78 @@ def metrics_from_grains(g, n_sites, defects=None, voxel_size=None, rng_seed=None
     }
 
 
+def grains_distributed(ctx, all_gather, theta_threshold=0.5):
+    """Grains of a lattice that is split into z-slabs over several contexts (one per rank), in the form
+    Context.grains() returns for a whole lattice — the reference's clusters (utils.py:28-84) in its
+    order — identical on every rank.
+
+    Every slab labels its owned planes plus 2 ghost planes per cut face (cet_grains_label).  A grain
+    that crosses a cut is a local component on both sides, and the two slabs give the SAME sites of
+    the 2 planes below the cut two labels: the pairs (label below, label above) are the edges that
+    join local components into grains.  They are gathered (a few thousand integers per cut), the
+    components of that small graph are found on the host, and the per-component statistics (voxel
+    counts of owned sites, bounding boxes) are added up per grain.
+
+    ctx: this rank's Context (ghost planes current, i.e. after the sweep's exchange);
+    all_gather(obj) -> list of every rank's obj in rank order (e.g. torch.distributed.all_gather_object
+    wrapped; see campaign.run_cet_sublattice)."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    loc = ctx.grains_local(theta_threshold)
+    i_begin, i_end = ctx.i_begin, ctx.i_end
+    n0 = ctx.n0
+    # the 2 owned planes below my upper cut, as I label them; and the neighbour's 2 planes below my lower
+    # cut (ghosts here), as I label them
+    mine_top = ctx.grain_label_planes(i_end - 2, i_end) if i_end < n0 else None
+    ghost_below = ctx.grain_label_planes(i_begin - 2, i_begin) if i_begin > 0 else None
+    tops = all_gather(mine_top)                         # tops[r] = rank r's labels of its top 2 owned planes
+    pairs = np.zeros((0, 2), np.int64)
+    if ghost_below is not None:
+        theirs = tops[ctx.rank - 1]
+        occ = ghost_below >= 0
+        pairs = np.unique(np.stack([theirs[occ].astype(np.int64), ghost_below[occ].astype(np.int64)], axis=1), axis=0)
+    gathered = all_gather((loc, pairs))
+    root = np.concatenate([g[0]["root"] for g in gathered])
+    size = np.concatenate([g[0]["size"] for g in gathered])
+    lo = np.concatenate([g[0]["box_lo"] for g in gathered]).astype(np.int64)
+    hi = np.concatenate([g[0]["box_hi"] for g in gathered]).astype(np.int64)
+    edges = np.concatenate([g[1] for g in gathered])
+    # local components that share a global root index on two ranks do not exist (a root is the smallest
+    # LOCAL site of the component, and each rank reports it as a global index of its own labelling), but a
+    # component is reported by every rank that labelled any of its sites: ids = unique (rank, root) pairs
+    owner = np.concatenate([np.full(len(g[0]["root"]), r, np.int64) for r, g in enumerate(gathered)])
+    key = owner * (np.int64(1) << 40) + root
+    order = np.argsort(key)
+    key, root, size, lo, hi, owner = key[order], root[order], size[order], lo[order], hi[order], owner[order]
+
+    def node(rank_of, roots):
+        return np.searchsorted(key, rank_of * (np.int64(1) << 40) + roots)
+
+    n = len(key)
+    if n == 0:
+        z = np.zeros((0, 3), np.int32)
+        return dict(n=0, root=np.zeros(0, np.int32), size=np.zeros(0, np.int32), box_lo=z, box_hi=z)
+    if len(edges):
+        e_rank = np.concatenate([np.full(len(g[1]), r, np.int64) for r, g in enumerate(gathered)])
+        a = node(e_rank - 1, edges[:, 0])               # the lower slab's component ...
+        b = node(e_rank, edges[:, 1])                   # ... is the same grain as the upper slab's
+        graph = coo_matrix((np.ones(len(a), np.int8), (a, b)), shape=(n, n))
+    else:
+        graph = coo_matrix((n, n), dtype=np.int8)
+    n_comp, comp = connected_components(graph, directed=False)
+    g_size = np.bincount(comp, weights=size, minlength=n_comp).astype(np.int64)
+    big = np.iinfo(np.int64).max
+    g_lo = np.full((n_comp, 3), big, np.int64); g_hi = np.full((n_comp, 3), -1, np.int64)
+    has = size > 0
+    np.minimum.at(g_lo, comp[has], lo[has]); np.maximum.at(g_hi, comp[has], hi[has])
+    g_root = np.full(n_comp, big, np.int64)
+    np.minimum.at(g_root, comp, root)                   # = the grain's smallest site: its owner's component is rooted there
+    keep = g_size > 0
+    order = np.argsort(g_root[keep], kind="stable")
+    return dict(n=int(keep.sum()), root=g_root[keep][order].astype(np.int64), size=g_size[keep][order].astype(np.int32),
+                box_lo=g_lo[keep][order].astype(np.int32), box_hi=g_hi[keep][order].astype(np.int32))
+
+
 def _resident(state, theta, phi, device=0):
     state = np.asarray(state)
     if state.ndim != 3 or len(set(state.shape)) != 1:

@@ -195,7 +195,9 @@ int cet_defects_refresh(cet_ctx *ctx, const double *draws, int64_t n_draws, uint
 
 /* ---- utils.get_clusters / metrics.compute_metrics (utils.py:28-84,104-111; metrics.py:41-96) ----
  * Grains = connected components of occupied sites (state != 0) joined by the 14-offset
- * neighbourhood with misorientation < theta_threshold.  Whole-lattice contexts only. */
+ * neighbourhood with misorientation < theta_threshold.  On a slab (ghost planes current) the labels are
+ * local components of the owned planes + 2 ghost planes per cut face, roots are GLOBAL site indices and
+ * the statistics count owned voxels; metrics.grains_distributed joins them across slabs. */
 int cet_grains_label(cet_ctx *ctx, double theta_threshold, int64_t *n_grains);
 /* criterion 0: misorientation of the orientation vectors < threshold (utils.py:51-56; cet_grains_label);
  * criterion 1: |theta1 - theta2| < threshold (utils.py:49-50, get_clusters(..., orientation_phi=None)). */
@@ -204,8 +206,11 @@ int cet_grains_label_ex(cet_ctx *ctx, double theta_threshold, int criterion, int
  * C-order site index (the grain's first voxel), voxel count, bounding box lo/hi [3*g + axis]. */
 int cet_grains_stats(cet_ctx *ctx, int64_t cap, int32_t *root, int32_t *size, int32_t *box_lo,
                      int32_t *box_hi);
-/* Label volume: root site index per occupied site, -1 for empty sites. */
+/* Label volume: root site index per occupied site, -1 for empty sites (owned planes). */
 int cet_grains_download_labels(cet_ctx *ctx, int32_t *labels);
+/* The same for global planes [i_lo, i_hi) within the labelled planes of a slab (owned + 2 ghost planes per
+ * cut face): what two neighbouring slabs compare to join the grains that cross their cut. */
+int cet_grains_download_planes(cet_ctx *ctx, int64_t i_lo, int64_t i_hi, int32_t *labels);
 
 /* Test hook: number of sites whose cached neighbour-state word differs from a fresh gather
  * (-1 when the cache is declared stale). */
