@@ -53,6 +53,7 @@ int tile_pass(cet_ctx *c, int p_lo, int p_hi, bool all);
 int stamp_fill(cet_ctx *c, int p_lo, int p_hi);
 int rates_rows_dirty_compact(cet_ctx *c, int p_lo, int p_hi, const uint32_t *stamp, int32_t *list, unsigned int *counter);
 int rates_rows_compact(cet_ctx *c, int p_lo, int p_hi);
+int rate_tables_ensure(cet_ctx *c);
 
 struct Record {          // one fired event
     int32_t src;         // local linear index of the source site
@@ -71,13 +72,15 @@ __device__ __forceinline__ unsigned long long claim_key(int rank, long long gsit
 }
 
 // ---- stream: one fire test per site against the resident rate sum --------------------------------
-// HBM-bound by design: 8 B/site and ~14 instructions/site.  One Philox4x32-10 block (128 bits)
-// serves the 16 sites of a thread, 8 bits each, as the leading digit of the site's uniform in base
-// 256: with x = R*tau and p = 1-exp(-x) <= x the site can only fire if digit <= floor(256 x), which
-// rejects all but ~1/256 + p of the sites after three fp64 instructions; the survivors evaluate p
-// exactly and, when digit == floor(256 p), draw the remaining digits from a second Philox block.
-// P(fire) = floor(256 p)/256 + (1/256) P(u' < frac(256 p)) = p exactly.
-constexpr int ST_THREADS = 256, ST_PER_THREAD = 16, ST_TILE = ST_THREADS * ST_PER_THREAD, ST_SURV = 1024;
+// HBM-bound by design: 8 B/site.  A thread owns 8 sites of a 2048-site tile of one plane (four
+// coalesced 16-byte loads) and one Philox4x32-10 block (128 bits) = one 16-bit digit per site, the
+// leading digit of the site's uniform in base 65536: with x = R*tau and p = 1-exp(-x) <= x the site
+// can only fire if digit <= floor(65536 x), which rejects all but ~p of the sites after three fp64
+// instructions; the survivors evaluate p exactly and, when digit == floor(65536 p), draw the
+// remaining digits from a second Philox block.  P(fire) = floor(65536 p)/65536 + P(u' < frac)/65536 = p.
+// Fired sites are staged in 2 KB of shared memory and appended with one list reservation per CTA;
+// 6 CTAs per SM stay resident (96 KB of loads in flight per SM).
+constexpr int ST_THREADS = 256, ST_PER_THREAD = 8, ST_TILE = ST_THREADS * ST_PER_THREAD, ST_STAGE = 512;
 
 struct StreamArgs {
     const double *site_rate, *dep_rate;   // dep_rate: plane of the global top (NaN = no event)
@@ -98,24 +101,20 @@ struct StreamArgs {
 // expm1 and a second Philox block, and inlining it costs the streaming loop its occupancy).
 __device__ __noinline__ bool stream_fire_exact(double x, double d, uint64_t seed, uint64_t gsite, uint32_t sweep)
 {
-    const double p256 = -expm1(-x) * 256.0;
-    const double f = floor(p256);
+    const double p16 = -expm1(-x) * 65536.0;
+    const double f = floor(p16);
     if (d != f) return d < f;
     double u_rest, unused;                              // leading digit ties: the rest of the uniform decides
     philox_u2(seed, gsite, sweep, STREAM_FIRE_REST, &u_rest, &unused);
-    return u_rest < p256 - f;
+    return u_rest < p16 - f;
 }
 
-__global__ void __launch_bounds__(ST_THREADS, 4) sweep_stream_kernel(const __grid_constant__ StreamArgs a)
+__global__ void __launch_bounds__(ST_THREADS, 6) sweep_stream_kernel(const __grid_constant__ StreamArgs a)
 {
     __shared__ double s_sum[ST_THREADS / 32], s_max[ST_THREADS / 32];
-    // survivors of the pre-filter (beyond ST_SURV they are tested in place) and fired sites of this tile
-    __shared__ int s_surv_q[ST_SURV];
-    __shared__ double s_surv_x[ST_SURV];
-    __shared__ uint8_t s_surv_d[ST_SURV];
-    __shared__ int s_list[ST_TILE];
-    __shared__ unsigned int s_cnt, s_base, s_nsurv;
-    if (threadIdx.x == 0) { s_cnt = 0; s_nsurv = 0; }
+    __shared__ int s_list[ST_STAGE];
+    __shared__ unsigned int s_cnt, s_base;
+    if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     const int pl = blockIdx.x / a.tiles_per_plane, tile = blockIdx.x % a.tiles_per_plane;
     const int p = a.p_lo + pl;
@@ -123,7 +122,7 @@ __global__ void __launch_bounds__(ST_THREADS, 4) sweep_stream_kernel(const __gri
     const double tau = a.ss->terminated ? 0.0 : a.ss->tau;
     const int64_t base = (int64_t)p * a.plane_sites;
     // site e of this thread: pairs interleaved across the warp so that every load is a coalesced
-    // 512-byte warp access: q(e) = tile*ST_TILE + w*512 + (e/2)*64 + lane*2 + (e&1)
+    // 512-byte warp access: q(e) = tile*ST_TILE + w*256 + (e/2)*64 + lane*2 + (e&1)
     const int qw = tile * ST_TILE + w * (32 * ST_PER_THREAD) + lane * 2;
     double R[ST_PER_THREAD];
     const bool vec = (a.plane_sites & 1) == 0;                       // every plane then starts 16-byte aligned
@@ -131,7 +130,7 @@ __global__ void __launch_bounds__(ST_THREADS, 4) sweep_stream_kernel(const __gri
     for (int m = 0; m < ST_PER_THREAD / 2; ++m) {
         const int q = qw + m * 64;
         if (vec && q + 1 < a.plane_sites) {
-            const double2 v = *reinterpret_cast<const double2 *>(a.site_rate + base + q);
+            const double2 v = __ldcs(reinterpret_cast<const double2 *>(a.site_rate + base + q));
             R[2 * m] = v.x; R[2 * m + 1] = v.y;
         } else {
             R[2 * m] = q < a.plane_sites ? a.site_rate[base + q] : 0.0;
@@ -151,40 +150,53 @@ __global__ void __launch_bounds__(ST_THREADS, 4) sweep_stream_kernel(const __gri
     double rsum = 0.0, rmax = 0.0;
 #pragma unroll
     for (int e = 0; e < ST_PER_THREAD; ++e) { rsum += R[e]; rmax = fmax(rmax, R[e]); }
-    // stage 1: digit pre-filter; survivors (a few per cent) are queued for the exact test
+    unsigned fmask = 0;
     if (tau > 0.0 && rmax > 0.0) {
         const uint32_t tid_in_plane = (uint32_t)(tile * ST_THREADS + threadIdx.x);
         const u32x4 r = philox4x32_10(u32x4{tid_in_plane, (uint32_t)(a.i_off + p), a.sweep, (uint32_t)STREAM_FIRE},
                                       (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
         const uint32_t words[4] = {r.x, r.y, r.z, r.w};
-        const double tau256 = tau * 256.0;
+        const double tau16 = tau * 65536.0;
 #pragma unroll
         for (int e = 0; e < ST_PER_THREAD; ++e) {
-            const uint32_t digit = (words[e >> 2] >> (8 * (e & 3))) & 0xFFu;
+            const uint32_t digit = (words[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
             const double d = __hiloint2double(0x43300000, (int)digit) - 4503599627370496.0;   // (double)digit
-            if (d <= R[e] * tau256) {                           // else digit > floor(256 x) >= floor(256 p): cannot fire
-                const unsigned int slot = atomicAdd(&s_nsurv, 1u);
+            if (d <= R[e] * tau16) {                            // else digit > floor(65536 x) >= floor(65536 p): cannot fire
                 const int site = qw + (e >> 1) * 64 + (e & 1);
-                if (slot < ST_SURV) {
-                    s_surv_q[slot] = site; s_surv_x[slot] = R[e] * tau; s_surv_d[slot] = (uint8_t)digit;
-                } else if (stream_fire_exact(R[e] * tau, d, a.seed,
-                                             (uint64_t)(a.i_off + p) * (uint64_t)a.plane_sites + (uint64_t)site, a.sweep)) {
-                    s_list[atomicAdd(&s_cnt, 1u)] = (int32_t)(base + site);
-                }
+                if (stream_fire_exact(R[e] * tau, d, a.seed, (uint64_t)(a.i_off + p) * (uint64_t)a.plane_sites + (uint64_t)site, a.sweep))
+                    fmask |= 1u << e;
             }
         }
     }
     rsum = warp_sum(rsum);
     rmax = warp_max(rmax);
     if (lane == 0) { s_sum[w] = rsum; s_max[w] = rmax; }
-    __syncthreads();
-    // stage 2: exact test of the survivors, converged
-    for (unsigned int q = threadIdx.x; q < min(s_nsurv, (unsigned)ST_SURV); q += ST_THREADS) {
-        const int site = s_surv_q[q];
-        const double d = (double)s_surv_d[q];
-        if (stream_fire_exact(s_surv_x[q], d, a.seed, (uint64_t)(a.i_off + p) * (uint64_t)a.plane_sites + (uint64_t)site,
-                              a.sweep))
-            s_list[atomicAdd(&s_cnt, 1u)] = (int32_t)(base + site);
+    // fired sites: staged per CTA (one global list reservation per CTA: a reservation per warp would put
+    // ~4e5 atomics per sweep on one address); a CTA with more than ST_STAGE of them appends the rest directly
+    if (__ballot_sync(0xffffffffu, fmask != 0)) {
+        const int mine = __popc(fmask);
+        int inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += u;
+        }
+        unsigned int q0 = 0;
+        if (lane == 31) q0 = atomicAdd(&s_cnt, (unsigned)inc);
+        q0 = __shfl_sync(0xffffffffu, q0, 31) + (unsigned)(inc - mine);
+        while (fmask) {
+            const int e = __ffs(fmask) - 1;
+            fmask &= fmask - 1;
+            const int32_t site = (int32_t)(base + qw + (e >> 1) * 64 + (e & 1));
+            if (q0 < ST_STAGE) {
+                s_list[q0] = site;
+            } else {
+                const unsigned int g = atomicAdd(&a.ss->n_fired, 1u);
+                if (g < a.cap_fired) a.fired[g] = site;
+                else a.ss->overflow = 1;
+            }
+            ++q0;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -192,10 +204,13 @@ __global__ void __launch_bounds__(ST_THREADS, 4) sweep_stream_kernel(const __gri
         for (int q = 0; q < ST_THREADS / 32; ++q) { t += s_sum[q]; m = fmax(m, s_max[q]); }
         a.blk_sum[blockIdx.x] = t;
         a.blk_max[blockIdx.x] = m;
-        s_base = s_cnt ? atomicAdd(&a.ss->n_fired, s_cnt) : 0u;
+        const unsigned int n = min(s_cnt, (unsigned)ST_STAGE);
+        s_base = n ? atomicAdd(&a.ss->n_fired, n) : 0u;
     }
+    const unsigned int n_staged = min(s_cnt, (unsigned)ST_STAGE);
+    if (n_staged == 0) return;
     __syncthreads();
-    for (unsigned int q = threadIdx.x; q < s_cnt; q += ST_THREADS) {
+    for (unsigned int q = threadIdx.x; q < n_staged; q += ST_THREADS) {
         if (s_base + q < a.cap_fired) a.fired[s_base + q] = s_list[q];
         else a.ss->overflow = 1;
     }
@@ -213,7 +228,53 @@ struct PickArgs {
     unsigned long long *claim;
     uint64_t seed;
     uint32_t sweep;
+    // compact tile state (NULL: enumerate with site_events from vox / v / T)
+    const uint8_t *cvox;
+    const double *pairop, *tab;
 };
+
+// The events of site s in the reference's list order from the compact tile state — the arithmetic of
+// the refresh kernels (tile_site_prep / tile_pair_rate), so the rates add up to the resident sum bit for
+// bit.  All 14 class codes and then all pair operands are requested before any is used: two memory
+// round trips per site instead of one per neighbour.  emit(type, slot, rate, atom) as site_events.
+template <class F>
+__device__ __forceinline__ void site_events_compact(const PickArgs &a, int s, int i, int j, int k, F &&emit)
+{
+    const int L = a.g.L;
+    const unsigned inb = inbounds_mask(i, j, k, a.g.n0, L);
+    const unsigned c = a.cvox[s];
+    unsigned b[14];
+#pragma unroll
+    for (int o = 0; o < 14; ++o)
+        b[o] = (inb >> o & 1u) ? (unsigned)a.cvox[s + (CET_NB_DI(o) * L + CET_NB_DJ(o)) * L + CET_NB_DK(o)] & 15u : 0u;
+    const unsigned code = c & 15u;
+    double T_self = 1.0, T_m = 1.0, T_p = 1.0;
+    if (code == TC_EMPTY) {
+        T_self = a.pairop[s];
+        T_m = k > 0 ? a.g.T[s - 1] : T_self;
+        T_p = k < L - 1 ? a.g.T[s + 1] : T_self;
+    } else {
+        T_self = a.g.T[s];
+    }
+    uint64_t w = 0;
+#pragma unroll
+    for (int o = 0; o < 14; ++o) w |= (uint64_t)b[o] << (4 * o);
+    const TilePrep q = tile_site_prep(a.P, a.tab, w, c, T_self, T_m, T_p);
+    double op[14];
+#pragma unroll
+    for (int o = 0; o < 14; ++o)
+        op[o] = (q.pm >> (4 * o) & 1u) ? a.pairop[s + (CET_NB_DI(o) * L + CET_NB_DJ(o)) * L + CET_NB_DK(o)] : 0.0;
+    if (q.sum0 != 0.0) emit((int)CET_EV_NUC, -1, q.sum0, a.P.states_w);
+    const int self_state = a.g.vox[s] & 0x0F;
+#pragma unroll
+    for (int o = 0; o < 14; ++o) {
+        if (!(q.pm >> (4 * o) & 1u)) continue;
+        const double rate = tile_pair_rate(a.P, a.tab, q.is_emp, q.A, q.B, op[o]);
+        if (rate == 0.0) continue;
+        if (q.is_emp) emit((int)CET_EV_ATT, o, rate, b[o] == TC_W ? a.P.states_w : b[o] == TC_RE ? a.P.states_re : a.P.states_c);
+        else emit((int)CET_EV_DIFF, o, rate, self_state);
+    }
+}
 
 __global__ void __launch_bounds__(128) sweep_pick_kernel(const __grid_constant__ PickArgs a)
 {
@@ -243,12 +304,15 @@ __global__ void __launch_bounds__(128) sweep_pick_kernel(const __grid_constant__
             cum = dep; ety = CET_EV_DEP; eatom = a.P.states_w;
             if (cum >= x) found = true;
         }
-        if (!found)
-            site_events(a.g, a.P, i, j, k, [&](int ty, int slot, double rate, int atom) {
-                if (found) return;
-                cum += rate; ety = ty; eslot = slot; eatom = atom;
-                if (cum >= x) found = true;
-            });
+        auto take = [&](int ty, int slot, double rate, int atom) {
+            if (found) return;
+            cum += rate; ety = ty; eslot = slot; eatom = atom;
+            if (cum >= x) found = true;
+        };
+        if (!found) {
+            if (a.cvox) site_events_compact(a, s, i, j, k, take);
+            else site_events(a.g, a.P, i, j, k, take);
+        }
         Record rec;
         rec.src = s;
         rec.theta = 0.0; rec.phi = 0.0;
@@ -355,7 +419,7 @@ struct ApplyArgs {
 };
 
 // the owner of `site` tells the neighbouring slab(s) what the site holds now
-__device__ __forceinline__ void delta_emit(const ApplyArgs &a, int site)
+__device__ __forceinline__ void delta_emit(const ApplyArgs &a, int site, uint8_t vox, double theta, double phi)
 {
     const int LL = a.L * a.L;
     const int p = site / LL;
@@ -368,19 +432,27 @@ __device__ __forceinline__ void delta_emit(const ApplyArgs &a, int site)
         const unsigned int q = atomicAdd(reinterpret_cast<unsigned int *>(buf), 1u);
         if (q >= a.delta_cap) { a.ss->overflow = 1; continue; }
         DeltaEntry e;
-        e.theta = a.theta[site]; e.phi = a.phi[site];
-        e.zidx = site - z0 * LL; e.vox = a.vox[site];
+        e.theta = theta; e.phi = phi;
+        e.zidx = site - z0 * LL; e.vox = vox;
         reinterpret_cast<DeltaEntry *>(buf + DELTA_HEADER)[q] = e;
     }
 }
 
-// cvox / pairop of a site that now holds `state` with orientation z component z
-__device__ __forceinline__ void tile_put(const ApplyArgs &a, int site, int state, double z)
+// cvox / pairop of a site whose voxel byte is now `vox` (orientation z component z, temperature T)
+__device__ __forceinline__ void tile_put(const ApplyArgs &a, int site, uint8_t vox, double z, double T)
 {
     if (!a.cvox) return;
-    const unsigned code = (unsigned)(a.tlut >> (4 * state)) & 15u;
-    a.cvox[site] = (uint8_t)((a.vox[site] & 0xF0) | code);
-    a.pairop[site] = code == TC_EMPTY ? a.T[site] : tile_pairop(a.P, code, 0.0, z);
+    const unsigned code = (unsigned)(a.tlut >> (4 * (vox & 0x0F))) & 15u;
+    a.cvox[site] = (uint8_t)((vox & 0xF0) | code);
+    a.pairop[site] = code == TC_EMPTY ? T : tile_pairop(a.P, code, 0.0, z);
+}
+// one site's new content: lattice, orientation vector, tile state
+__device__ __forceinline__ void site_write(const ApplyArgs &a, int site, uint8_t vox, double theta, double phi, const Vec4 &uv, double T)
+{
+    a.vox[site] = vox;
+    a.theta[site] = theta; a.phi[site] = phi;
+    a.v[site] = uv;
+    tile_put(a, site, vox, uv.z, T);
 }
 
 // A site changed state: request a refresh of the site and of its neighbours.  The refresh pass
@@ -427,51 +499,46 @@ __global__ void __launch_bounds__(128) sweep_apply_kernel(const __grid_constant_
         const bool owned = p >= a.own_lo && p < a.own_hi;
         if (owned) ++fired;
         const bool complete = p >= a.c_lo && p < a.c_hi && pt >= a.c_lo && pt < a.c_hi;
+        // Everything the event reads — both claims, both voxel bytes, the source's temperature — is requested
+        // here in one batch; the write phase below works from registers (the kernel is a latency chain per
+        // event: every dependent global read costs a DRAM round trip under ~1e6 scattered accesses).
+        const bool two = ety == CET_EV_DIFF;
         const unsigned long long cs = a.claim[s];
-        const unsigned long long ct = (ety == CET_EV_DIFF) ? a.claim[tgt] : key;
+        const unsigned long long ct = two ? a.claim[tgt] : key;
+        const uint8_t vox_s = a.vox[s];
+        const uint8_t vox_t = two ? a.vox[tgt] : (uint8_t)0;
+        const double T_s = (two && a.cvox) ? a.T[s] : 0.0;              // a vacated site's pair operand is its temperature
         const bool win = complete && cs == key && ct == key;
         if (win) {
-            int upd = s;
-            const int src_state = a.vox[s] & 0x0F;                      // before the event
-            const Vec4 uv = unit_vec4(rec.theta, rec.phi);             // same bits as the source's resident vector
-            if (ety == CET_EV_DIFF) {                                    // kmc_simulation.py:292-303
-                a.vox[tgt] = (uint8_t)((a.vox[tgt] & 0xF0) | (a.vox[s] & 0x0F));
-                a.theta[tgt] = rec.theta; a.phi[tgt] = rec.phi;
-                a.v[tgt] = uv;
-                a.vox[s] = (uint8_t)(a.vox[s] & 0xF0);
-                a.theta[s] = 0.0; a.phi[s] = 0.0;
-                a.v[s] = Vec4{0.0, 0.0, 1.0, 0.0};
-                tile_put(a, tgt, src_state, uv.z);
-                tile_put(a, s, 0, 1.0);
-                upd = tgt;
-            } else {                                                     // dep / nuc / att
-                a.vox[s] = (uint8_t)((a.vox[s] & 0xF0) | eatom);
-                a.theta[s] = rec.theta; a.phi[s] = rec.phi;
-                a.v[s] = uv;
-                tile_put(a, s, eatom, uv.z);
-                if (ety == CET_EV_NUC && owned) ++nuc;
-            }
-            int upd_state = ety == CET_EV_DIFF ? src_state : eatom;      // what the filled site holds
+            const int src_state = vox_s & 0x0F;                         // before the event
+            Vec4 uv = unit_vec4(rec.theta, rec.phi);                    // same bits as the source's resident vector
+            const Vec4 none = Vec4{0.0, 0.0, 1.0, 0.0};
+            double th = rec.theta, ph = rec.phi;
+            // the site that receives the atom: the target of a diffusion event, the source otherwise
+            const int upd = two ? tgt : s;
+            uint8_t vox_u = two ? (uint8_t)((vox_t & 0xF0) | src_state) : (uint8_t)((vox_s & 0xF0) | eatom);
+            int upd_state = two ? src_state : eatom;
+            if (ety == CET_EV_NUC && owned) ++nuc;
             if (a.defect_fraction > 0.0) {                               // :323-327
                 double u2, unused;
                 philox_u2(a.seed, (uint64_t)gsite, a.sweep, STREAM_DEFECT, &u2, &unused);
                 if (u2 < a.defect_fraction) {
-                    a.vox[upd] = (uint8_t)((a.vox[upd] & 0xF0) | a.P.defect_id);
-                    a.theta[upd] = 0.0; a.phi[upd] = 0.0;
-                    a.v[upd] = Vec4{0.0, 0.0, 1.0, 0.0};
-                    tile_put(a, upd, a.P.defect_id, 1.0);
+                    vox_u = (uint8_t)((vox_u & 0xF0) | a.P.defect_id);
+                    th = 0.0; ph = 0.0; uv = none;
                     upd_state = a.P.defect_id;
                 }
             }
+            site_write(a, upd, vox_u, th, ph, uv, 0.0);                  // dep / nuc / att / diff target (:280-317)
+            if (two) site_write(a, s, (uint8_t)(vox_s & 0xF0), 0.0, 0.0, none, T_s);     // :299-301
             if (owned) ++applied;
-            if (ety == CET_EV_DIFF) {
+            if (two) {
                 site_changed(a, s, src_state, 0);
                 site_changed(a, tgt, 0, upd_state);
-                delta_emit(a, s);
-                delta_emit(a, tgt);
+                delta_emit(a, s, (uint8_t)(vox_s & 0xF0), 0.0, 0.0);
+                delta_emit(a, tgt, vox_u, th, ph);
             } else {
                 site_changed(a, s, 0, upd_state);
-                delta_emit(a, s);
+                delta_emit(a, s, vox_u, th, ph);
             }
         }
         // release the claims this event holds (only the top claimant of a site clears it)
@@ -498,11 +565,7 @@ __global__ void __launch_bounds__(128) delta_scatter_kernel(const __grid_constan
         const DeltaEntry e = ent[q];
         const int site = g0 * LL + e.zidx;
         const int old_state = a.vox[site] & 0x0F, new_state = (int)(e.vox & 0x0Fu);
-        a.vox[site] = (uint8_t)e.vox;
-        a.theta[site] = e.theta; a.phi[site] = e.phi;
-        const Vec4 uv = unit_vec4(e.theta, e.phi);
-        a.v[site] = uv;
-        tile_put(a, site, new_state, uv.z);
+        site_write(a, site, (uint8_t)e.vox, e.theta, e.phi, unit_vec4(e.theta, e.phi), a.T[site]);
         site_changed(a, site, old_state, new_state);
     }
 }
@@ -685,6 +748,7 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
         a.P = c->rp; a.ss = c->sweep; a.fired = c->fired; a.cap_fired = (unsigned int)c->cap_fired;
         a.records = (Record *)c->records; a.claim = c->claim;
         a.seed = sp->seed; a.sweep = (uint32_t)c->sweep_index;
+        a.cvox = tiled ? c->cvox : nullptr; a.pairop = c->pairop; a.tab = c->rate_tab;
         ProfScope ps(c, PROF_PICK);
         sweep_pick_kernel<<<sparse_grid, 128, 0, c->stream>>>(a);
     }
@@ -812,6 +876,7 @@ extern "C" int cet_sweep_run(cet_ctx *c, int64_t n_sweeps, const cet_sweep_param
         tiled = f == 0.0;
     }
     if (tiled) {
+        if (int rc = rate_tables_ensure(c)) return rc;      // the pick kernel reads the K_eff / E_tot tables
         c->nst_valid = false;                // the tile path keeps no neighbour cache
         if (c->world > 1) if (int rc = comm_delta_alloc(c)) return rc;
     } else {
