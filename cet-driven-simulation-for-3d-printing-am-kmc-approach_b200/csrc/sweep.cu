@@ -416,6 +416,7 @@ struct ApplyArgs {
     // face's send buffer (NULL: no neighbour on that side)
     unsigned char *delta_lo, *delta_hi;
     unsigned int delta_cap;
+    int probe;             // timing probes (cet_debug_flags 64 / 128): 1 = skip the stamps, 2 = skip the field writes — results invalid
 };
 
 // the owner of `site` tells the neighbouring slab(s) what the site holds now
@@ -449,6 +450,7 @@ __device__ __forceinline__ void tile_put(const ApplyArgs &a, int site, uint8_t v
 // one site's new content: lattice, orientation vector, tile state
 __device__ __forceinline__ void site_write(const ApplyArgs &a, int site, uint8_t vox, double theta, double phi, const Vec4 &uv, double T)
 {
+    if (a.probe & 2) return;
     a.vox[site] = vox;
     a.theta[site] = theta; a.phi[site] = phi;
     a.v[site] = uv;
@@ -464,6 +466,7 @@ __device__ __forceinline__ void site_write(const ApplyArgs &a, int site, uint8_t
 // gather from the refresh, -0.13 ms, but costs the apply kernel +0.52 ms per sweep at 6.6e5 events.)
 __device__ __forceinline__ void site_changed(const ApplyArgs &a, int site, int, int)
 {
+    if (a.probe & 1) return;
     const int LL = a.L * a.L;
     const int p = site / LL, j = (site / a.L) % a.L, k = site % a.L;
     atomicOr(&a.stamp[site >> 5], 1u << (site & 31));
@@ -767,6 +770,7 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
         b.delta_lo = (deltas && c->rank > 0) ? (unsigned char *)c->delta_send[0] : nullptr;
         b.delta_hi = (deltas && c->rank < c->world - 1) ? (unsigned char *)c->delta_send[1] : nullptr;
         b.delta_cap = (unsigned int)c->delta_cap;
+        b.probe = (c->debug_flags >> 6) & 3;
         if (b.delta_lo) CET_CUDA(cudaMemsetAsync(b.delta_lo, 0, DELTA_HEADER, c->stream));
         if (b.delta_hi) CET_CUDA(cudaMemsetAsync(b.delta_hi, 0, DELTA_HEADER, c->stream));
         apply_args = b;
