@@ -10,11 +10,11 @@ One step = one synchronous-sublattice sweep over the whole lattice (csrc/sweep.c
 against its resident rate sum, event pick + conflict resolution + apply for the fired sites,
 neighbour-rate refresh of the sites the events touched, totals for the next time increment, and
 (N > 1) the halo exchange.
-Workload: the 'half-grown' synthetic lattice of SURVEY §8(d)(ii).
-    default / --scaling strong : the lattice the metric names, L^3 = 512^3, split into z-slabs over
-                                 the N GPUs (BASELINE.json: "512^3 at 1/2/4/8 B200"); --L 1024 is
-                                 BASELINE configs[3]
-    --scaling weak             : N GPUs hold (L N) x L x L, L planes each
+Workload: the 'half-grown' synthetic lattice of SURVEY §8(d)(ii), 512^3 at N = 1 (the lattice the
+metric names).
+    default / --scaling weak   : N GPUs hold (512 N) x 512 x 512 split into z-slabs, 512 planes each
+    --scaling strong           : the same L^3 lattice split into z-slabs over the N GPUs: --L 512 is the
+                                 metric's lattice at 2/4/8 GPUs, --L 1024 is BASELINE configs[3]
     --thermal laser            : BASELINE configs[2] — the thermal step is thermal_solver.update_temperature
                                  (laser source + latent heat, thermal_solver.py:36-105) with the melt pool
                                  moving along axis 1, driven between 20-sweep blocks (N = 1)
@@ -247,7 +247,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cetkmc", choices=["cetkmc", "reference"])
     ap.add_argument("--L", type=int, default=L_BENCH, help="edge length (strong) / sites per edge in a plane and planes per GPU (weak)")
-    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--scaling", default="weak", choices=["strong", "weak"])
     ap.add_argument("--thermal", default="cet", choices=["cet", "laser"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -97,15 +97,18 @@ def rate_params(impurity_c=0.0, states_w=1, states_re=2, states_c=3, overrides=N
     return p
 
 
-def thermal_params(dt=1e-6, nan_to_num=False) -> _lib.ThermalParams:
-    """cet_thermal_params with Python's exact doubles (thermal_solver.py:114-117)."""
+def thermal_params(dt=1e-6, nan_to_num=False, t_floor=None) -> _lib.ThermalParams:
+    """cet_thermal_params with Python's exact doubles (thermal_solver.py:114-117).  t_floor: lower clip
+    and NaN fill of a run whose substrate temperature is not constants.T_SUB (the G-R sweep): the
+    reference clips to the constant, which would lift a colder substrate to T_SUB at the first step and
+    change the gradient the run reports."""
     c = constants
     tp = _lib.ThermalParams()
     tp.dt_alpha = dt * ALPHA
     tp.inv_dx2 = 1.0 / (c.VOXEL_SIZE * c.VOXEL_SIZE)
-    tp.lo = float(c.T_SUB)
+    tp.lo = float(c.T_SUB if t_floor is None else min(t_floor, c.T_SUB))
     tp.hi = c.T_MELT * 1.1
-    tp.nan_value = float(c.T_SUB)                     # kmc_simulation.py:249
+    tp.nan_value = tp.lo                              # kmc_simulation.py:249
     tp.nan_to_num = 1 if nan_to_num else 0
     return tp
 

@@ -183,7 +183,9 @@ def run_cet_sublattice(L=None, n_sweeps=2000, temp=None, defect_fraction=0.0, n_
         sp.events_per_sweep = float(events_per_sweep if events_per_sweep is not None else 0.005 * L ** 3)
         sp.p_max, sp.defect_fraction = float(p_max), float(defect_fraction)
         sp.thermal_every = 0 if laser else int(thermal_every)
-        tp = None if laser else thermal_params(_ks.THERMAL_DT, nan_to_num=True)
+        tp = None if laser else thermal_params(_ks.THERMAL_DT, nan_to_num=True, t_floor=temp)
+        if laser and int(thermal_every) <= 0:
+            raise ValueError("run_cet_sublattice: the laser variant needs thermal_every >= 1")
         if laser:
             l_dt = float(laser.get("dt", _ks.THERMAL_DT))
             l_pos = [float(x) for x in laser.get("start", (0.0, 0.0))]

@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--n0", type=int, default=0)
     ap.add_argument("--sweeps", type=int, default=12)
     ap.add_argument("--eps", type=float, default=0.01)
+    ap.add_argument("--flags", type=int, default=0, help="cet_debug_flags of the slab run (the single-GPU run uses the default kernels)")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -48,6 +49,7 @@ def main():
 
     packed, th, ph, T = _synth.half_grown(L, seed=99, grain=4, planes=(i_begin, i_end), n0=n0)
     ctx = cetkmc.Context(L=L, n0=n0, device=local, i_begin=i_begin, i_end=i_end, halo=SWEEP_HALO)
+    ctx.debug_flags(args.flags)
     ctx.set_rate_params(rate_params(0.1))
     ctx.upload_packed(packed)
     ctx.upload(theta=th, phi=ph, T=T)
