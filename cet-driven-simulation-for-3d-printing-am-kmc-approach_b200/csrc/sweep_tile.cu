@@ -241,7 +241,7 @@ __device__ __forceinline__ void tile_eval_serial(const TileArgs &a, const double
 }
 
 template <int STAGE, int EVAL>
-__global__ void __launch_bounds__(TL_THREADS, EVAL == 0 ? 4 : 5)
+__global__ void __launch_bounds__(TL_THREADS, EVAL == 0 ? 3 : 4)
     rates_tile3d_kernel(const __grid_constant__ TileArgs a, const __grid_constant__ CUtensorMap tm_vox,
                         const __grid_constant__ CUtensorMap tm_po)
 {
@@ -584,6 +584,9 @@ static int tile_maps_ensure(cet_ctx *c)
     return 0;
 }
 
+// rows that a tensor map can describe (16-byte strides for the 1-byte array) and that fill a box
+bool tile_tma_ok(const cet_ctx *c) { return c->n1 % 16 == 0 && c->n1 >= 64; }
+
 template <int STAGE, int EVAL>
 static int tile_launch(cet_ctx *c, const TileArgs &a, int *blocks_per_sm)
 {
@@ -626,10 +629,10 @@ int tile_pass(cet_ctx *c, int p_lo, int p_hi, bool all)
     a.njb = (int)((c->n1 + TL_J - 1) / TL_J); a.nkb = (int)((c->n2 + TL_K - 1) / TL_K);
     a.n_tiles = ((p_hi - p_lo + TL_I - 1) / TL_I) * a.njb * a.nkb;
     a.mode = all ? TM_ALL : 0;
-    // staging: 16-byte vector loads when the rows allow it, scalar loads otherwise; TMA boxes on request
-    // (debug flag 16; measured slower for these short-row boxes, profiles/)
-    const bool aligned = c->n1 % 16 == 0 && c->n1 >= 64;
-    const int stage = (aligned && (c->debug_flags & 16)) ? 0 : (aligned && !(c->debug_flags & 1)) ? 1 : 2;
+    // staging: 3-D TMA boxes when the rows allow it (L % 16 == 0), scalar loads otherwise; 16-byte vector
+    // loads on request (debug flag 16; measured 2.7x slower than TMA for the same bytes, profiles/)
+    const bool aligned = tile_tma_ok(c);
+    const int stage = !aligned || (c->debug_flags & 1) ? 2 : (c->debug_flags & 16) ? 1 : 0;
     const bool serial = (c->debug_flags & 4) != 0;
     if (stage == 0) if (int rc = tile_maps_ensure(c)) return rc;
     int *bps = &c->tile_blocks[stage * 2 + (serial ? 1 : 0)];

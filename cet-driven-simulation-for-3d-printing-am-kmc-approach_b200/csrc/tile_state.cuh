@@ -31,7 +31,7 @@ constexpr int TL_VK = 64, TL_VK0 = 16;                   // staged cvox bytes pe
 constexpr int TL_PK = TL_K + 4, TL_PK0 = 2;              // staged pairop doubles per row
 constexpr int TL_VBYTES = TL_HI * TL_HJ * TL_VK;         // 6 144
 constexpr int TL_PBYTES = TL_HI * TL_HJ * TL_PK * 8;     // 27 648
-constexpr int TL_THREADS = 128, TL_WARPS = TL_THREADS / 32;
+constexpr int TL_THREADS = 256, TL_WARPS = TL_THREADS / 32;
 
 enum { TC_OUTSIDE = 0, TC_OTHER = 1, TC_DEFECT = 3, TC_EMPTY = 8, TC_W = 9, TC_RE = 11, TC_C = 13 };
 

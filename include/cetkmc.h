@@ -216,12 +216,15 @@ int cet_grains_download_planes(cet_ctx *ctx, int64_t i_lo, int64_t i_hi, int32_t
  * (-1 when the cache is declared stale). */
 int cet_debug_nst_mismatches(cet_ctx *ctx, int64_t *n_bad);
 /* Test / profiling hook: which kernels keep the rate sums current in cet_sweep_run (all variants give
- * the same bits).  Default: list-driven gathers from the compact tile state (class codes + pair operands).
- * bit 1 (2): the gather refresh of the first design (neighbour-class cache + unit vectors);
- * bit 5 (32): the shared-memory tile kernel, staged by 16-byte vector loads, or with bit 4 (16) by 3-D TMA
- * boxes, or with bit 0 (1) by scalar loads; bit 2 (4): the tile kernel walks the 14 neighbour slots per lane
- * instead of compacting the pairs across the warp; bit 3 (8): dense rebuilds by the gather kernel of
- * rates.cu instead of the tile kernel. */
+ * the same bits).  Default: stamped sites are refreshed by list-driven gathers from the compact tile state
+ * (class codes + pair operands); the dense rebuild after a thermal step runs the shared-memory tile kernel
+ * staged by 3-D TMA boxes when L % 16 == 0, the dense gather kernel on the compact state otherwise.
+ * 2: the gather refresh + dense kernel of the first design (neighbour-class cache + unit vectors);
+ * 32: the tile kernel also for the refresh; 1: tile kernel staged by scalar loads, 16: by 16-byte vector loads;
+ * 4: the tile kernel walks the 14 neighbour slots per lane instead of compacting the pairs across the warp;
+ * 8: dense rebuilds by the first design's gather kernel; 65536: dense rebuilds by the compact gather kernel;
+ * 64 / 128: timing probes of the apply kernel (stamps / field writes skipped: results invalid);
+ * bits 8-15: stamped sites per warp and queue entry of the refresh, in units of 32 (0 = default 64). */
 int cet_debug_flags(cet_ctx *ctx, int flags);
 
 /* ---- per-kernel device timing: CUDA event pairs recorded on the context stream around every

@@ -1,8 +1,9 @@
 """GPU: synchronous-sublattice sweeps (csrc/sweep.cu, csrc/sweep_tile.cu) — invariants, determinism
 and level-3 parity (trajectory observables against the serial oracle within statistical bounds).
-Refresh variants (Context.debug_flags): COMPACT (default) = list-driven gathers from the compact tile state
-(class codes + pair operands); TILE = the shared-memory tile kernel (vector-load staging), TMA / SCALAR its
-other staging modes, SERIAL its per-lane pair loop; GATHER = the gather refresh of the first design
+Rate-maintenance variants (Context.debug_flags): COMPACT (default) = stamped sites refreshed by list-driven
+gathers from the compact tile state, dense rebuilds by the TMA-staged tile kernel when L % 16 == 0; TILE = the
+tile kernel for the refresh too (TMA staging), VECTOR / SCALAR its other staging modes, SERIAL its per-lane pair
+loop; DENSE_COMPACT = dense rebuilds by the compact gather kernel; GATHER = refresh + rebuild of the first design
 (neighbour-class cache + unit vectors)."""
 import numpy as np
 import pytest
@@ -17,8 +18,9 @@ def _sweep_params(cet, seed, L, eps=0.02, p_max=0.25, defect_fraction=0.0, therm
     return sp
 
 
-COMPACT, GATHER, TILE = 0, 2, 32
-SCALAR, SERIAL, TMA = TILE | 1, TILE | 4, TILE | 16
+COMPACT, GATHER, TILE, DENSE_COMPACT = 0, 2, 32, 65536
+SCALAR, SERIAL, VECTOR = TILE | 1, TILE | 4, TILE | 16
+TMA = TILE
 FUSED = COMPACT
 
 
@@ -91,7 +93,7 @@ def test_refresh_variants_agree(cet, L):
     and resident rates."""
     from cetkmc._config import thermal_params
     outs = []
-    for flags in (COMPACT, TILE, SCALAR, TMA, SERIAL, SERIAL | 16, GATHER, COMPACT | 8):
+    for flags in (COMPACT, DENSE_COMPACT, TILE, SCALAR, VECTOR, SERIAL, SERIAL | 16, GATHER, COMPACT | 8):
         ctx, st, th, ph, T, df = _setup(cet, L, flags=flags)
         res = ctx.sweep_run(7, _sweep_params(cet, 5, L, eps=0.01, p_max=0.2, defect_fraction=0.01, thermal_every=3),
                             thermal_params(1e-6, nan_to_num=True))
