@@ -1,0 +1,346 @@
+// rates_dense.cu — dense evaluation of every site's rate sum (the rebuild after a thermal step, an upload or a
+// parameter change) from the compact tile state: the rate kernel of kmc_event_rates.py:43-160 for the sweep path.
+//
+// The pass is bound by instruction issue and the FP64 pipe, not by HBM: an attachment pair
+// costs one fp64 exp (17 FP64 instructions = 34 pipe cycles per warp), a diffusion pair one reciprocal, and a
+// site next to a solid/empty interface owns up to 14 of them.  What the counters of the earlier kernels said
+// (997 warp instructions per 32 sites, only 110 of them FP64) is that everything AROUND the arithmetic has to
+// go, so this kernel is built to execute little else:
+//   * a CTA stages a 4 x 8 x 32 tile of cvox + pairop with its halo of 2 by two 3-D TMA boxes (zero fill
+//     outside the lattice = class code 0 = "outside": no bounds logic anywhere); neighbour classes and pair
+//     operands are LDS with immediate offsets from one base register per site;
+//   * warps are autonomous inside a tile (4 rows each).  Pass A reads the 15 class codes of a site, packs them
+//     4 bits per slot, and only CLASSIFIES: sites without events store 0, empty sites without an occupied
+//     neighbour evaluate their nucleation rate on the spot when they are the bulk of the row (the melt above the
+//     front), everything else is appended to the warp's list of its class — empty sites from the front,
+//     occupied sites from the back;
+//   * pass B evaluates the two lists 32 sites at a time, so a trip runs ONE class: the per-site half
+//     (tile_prep_emp / tile_prep_occ: one exp each) without the other class's lanes idling beside it, then
+//     every lane walks its own pair mask in slot order with the running sum in a register — no descriptors, no
+//     shared-memory round trip for operands or rates, and the association order of site_rate_sum for free.
+// The arithmetic is the shared inline code of site_rates.cuh / tile_state.cuh, so the result equals the
+// per-event code, the refresh kernels and the other dense kernels bit for bit (tests/test_gpu_sweep.py).
+#include <cuda.h>
+#include <algorithm>
+#include <utility>
+#include "ctx.cuh"
+#include "tile_state.cuh"
+#include "tma.cuh"
+
+namespace cet {
+
+int rate_tables_ensure(cet_ctx *c);      // rates.cu
+int tile_maps_ensure(cet_ctx *c);        // sweep_tile.cu
+int sm_count(cet_ctx *c);
+
+constexpr int DN_ROWS = TL_I * TL_J;                     // 32 rows of 32 sites per tile
+constexpr int DN_WROWS = DN_ROWS / TL_WARPS;             // rows per warp
+constexpr int DN_LIST = DN_WROWS * 32;                   // list slots per warp: every site is in at most one list
+constexpr int DN_INLINE_MIN = 12;                        // pass A evaluates pairless empty sites itself from this many per row on
+
+struct DenseWarpList {
+    uint64_t w[DN_LIST];                                 // class codes of the 14 neighbours, 4 bits per slot
+    uint32_t e[DN_LIST];                                 // tile-local site index (li << 8 | lj << 5 | lk) | own cvox byte << 16
+};
+struct DenseSmem {
+    double po[TL_HI * TL_HJ * TL_PK];                    // 128-byte aligned TMA destinations first
+    uint8_t vx[TL_VBYTES];
+    double tab[RT_TABLE_DOUBLES];
+    DenseWarpList wl[TL_WARPS];
+    int16_t dpb[16];                                     // [15 - o]: byte offset of neighbour slot o's pairop from the site's own
+    unsigned long long bar;
+    int tile[2];                                         // tile index of this / the next iteration (popped ahead of need)
+};
+
+struct DenseArgs {
+    const double *T;
+    double *site_rate, *dep_rate;
+    const double *tab;
+    unsigned int *queue;
+    cet_rate_params P;
+    int L, p_lo, p_hi, top_plane;
+    int njb, nkb, n_tiles;
+};
+
+template <int OFF>
+__device__ __forceinline__ unsigned lds_u8(uint32_t addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+template <int O>
+__device__ __forceinline__ unsigned dn_code(uint32_t vaddr)
+{
+    return lds_u8<(CET_NB_DI(O) * TL_HJ + CET_NB_DJ(O)) * TL_VK + CET_NB_DK(O)>(vaddr) & 15u;
+}
+template <int... O>
+__device__ __forceinline__ uint32_t dn_pack(uint32_t vaddr, int base, std::integer_sequence<int, O...>)
+{
+    return ((dn_code<O>(vaddr) << (4 * (O - base))) + ...);            // disjoint nibbles: + is |, and one LEA per slot
+}
+__device__ __forceinline__ int lds_s16(uint32_t addr)
+{
+    int v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// bits 4*o of a nibble mask -> bits 2*o
+__device__ __forceinline__ uint32_t nib_compress2(uint32_t x)
+{
+    x = (x | (x >> 2)) & 0x05050505u;
+    x = (x | (x >> 4)) & 0x00550055u;
+    return (x | (x >> 8)) & 0x5555u;
+}
+// Walk order of a site's pair mask: slot o at bit 30 - 2*o, so the leading set bit is the lowest slot and its
+// position is the BYTE offset of the slot's entry in the reversed 16-bit offset table (DenseSmem::dpb).
+__device__ __forceinline__ uint32_t pair_walk_mask(uint64_t pm)
+{
+    return __brev((nib_compress2((uint32_t)pm) | (nib_compress2((uint32_t)(pm >> 32)) << 16)) << 1);
+}
+
+// `sum += keep_rate(P, rate)` without the selects: rates are never negative and sum never -0 or NaN, so adding the
+// kept rate or nothing gives the same bits; for rate > threshold, `rate < inf` is a test of the high word.
+__device__ __forceinline__ void add_kept(const cet_rate_params &P, double &sum, double rate)
+{
+    asm("{\n"
+        ".reg .pred p;\n"
+        "setp.gt.f64 p, %1, %2;\n"
+        "setp.lt.and.s32 p, %3, 0x7ff00000, p;\n"
+        "@p add.rn.f64 %0, %0, %1;\n"
+        "}\n"
+        : "+d"(sum)
+        : "d"(rate), "d"(P.rate_threshold), "r"(__double2hiint(rate)));
+}
+
+// The pairs of one site in slot order, out of line: the rare sites with an Arrhenius argument outside fast_exp's range.
+template <bool ATT>
+__device__ __noinline__ double dn_pairs_slow(const cet_rate_params &P, const double *tab, const int16_t *dpb, uint32_t m, uint32_t base, double A,
+                                             double B, double sum)
+{
+    while (m) {
+        const int h = 31 - __clz(m);
+        m ^= 1u << h;
+        const double op = lds_f64(base + (uint32_t)(int)dpb[h >> 1]);
+        sum += ATT ? att_pair_rate_E(P, op, A, B, tab) : diff_pair_rate(P, A, B, op);
+    }
+    return sum;
+}
+
+// The pairs of one site in slot order.  m: pair_walk_mask; base: shared address of the site's own pairop;
+// dpb: shared address of the offset table.  ILP pairs are in flight per trip.
+template <bool ATT, int ILP>
+__device__ __forceinline__ double dn_pairs(const cet_rate_params &P, const DenseSmem &sm, const uint32_t m0, uint32_t base, uint32_t dpb, double A,
+                                           double B, const double sum0)
+{
+    uint32_t m = m0;
+    double sum = sum0;
+    int xmax = 0;                                                        // largest |Arrhenius argument| (high word) of the site
+    do {
+        double rate[ILP];
+        bool on[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            on[u] = u == 0 || m != 0u;
+            const int h = (u == 0 || on[u]) ? 31 - __clz(m) : 0;         // FLO: position of the leading bit
+            m &= (1u << h) - 1u;
+            double op = 0.0;
+            if (on[u]) op = lds_f64(base + (uint32_t)lds_s16(dpb + (uint32_t)h));
+            if (ATT) {                                                   // att_pair_rate_E (kmc_event_rates.py:147-157)
+                const double x = -op * A;
+                xmax = max(xmax, __double2hiint(x) & 0x7fffffff);
+                rate[u] = fast_exp_core(x, sm.tab + RT_EXP2) * B;
+            } else {                                                     // diff_pair_rate (:102-108)
+                const double neighbor_T = pymax(op, 1.0);
+                const double dT = fabs(A - neighbor_T);
+                const double denom = pymax(P.T_melt - neighbor_T, 1.0);
+                rate[u] = fma(0.1 * dT, rcp1(denom), 1.0) * B;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+            if (on[u]) add_kept(P, sum, rate[u]);
+    } while (m);
+    const bool bad = xmax >= 0x4085e000;                                 // !(|x| < 700) for some pair, NaN included: fast_exp's range
+    if (ATT && bad) sum = dn_pairs_slow<ATT>(P, sm.tab + RT_EXP2, sm.dpb, m0, base, A, B, sum0);
+    return sum;
+}
+
+template <int ILP>
+__global__ void __launch_bounds__(TL_THREADS, 4)
+    rates_dense_kernel(const __grid_constant__ DenseArgs a, const __grid_constant__ CUtensorMap tm_vox, const __grid_constant__ CUtensorMap tm_po)
+{
+    extern __shared__ unsigned char dense_dyn_smem[];
+    DenseSmem &sm = *reinterpret_cast<DenseSmem *>(dense_dyn_smem + ((1024u - (smem_u32(dense_dyn_smem) & 1023u)) & 1023u));
+    const cet_rate_params &P = a.P;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int L = a.L;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    for (int q = tid; q < RT_TABLE_DOUBLES; q += TL_THREADS) sm.tab[q] = a.tab[q];
+    if (tid < 14) sm.dpb[15 - tid] = (int16_t)((((int)c_nb_off[tid][0] * TL_HJ + c_nb_off[tid][1]) * TL_PK + c_nb_off[tid][2]) * 8);
+    if (tid == 0) {
+        mbar_init(&sm.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sm.tile[0] = (int)atomicAdd(a.queue, 1u);
+    }
+    __syncthreads();
+    DenseWarpList &wl = sm.wl[wid];
+    const uint32_t vx0 = smem_u32(sm.vx), po0 = smem_u32(sm.po), dpb0 = smem_u32(sm.dpb);
+    const int tiles_per_iblock = a.njb * a.nkb;
+
+    for (unsigned it = 0;; ++it) {
+        const int t = sm.tile[it & 1u];
+        if (t >= a.n_tiles) break;
+        const int kb = t % a.nkb, jb = (t / a.nkb) % a.njb, ib = t / tiles_per_iblock;
+        const int p0 = a.p_lo + TL_I * ib, j0 = TL_J * jb, k0 = TL_K * kb;
+        if (tid == 0) {
+            mbar_expect_tx(&sm.bar, (unsigned)(TL_VBYTES + TL_PBYTES));
+            tma_load_3d(sm.vx, &tm_vox, &sm.bar, k0 - TL_VK0, j0 - 2, p0 - 2);
+            tma_load_3d(sm.po, &tm_po, &sm.bar, k0 - TL_PK0, j0 - 2, p0 - 2);
+            sm.tile[(it + 1u) & 1u] = (int)atomicAdd(a.queue, 1u);       // read after the barrier that ends this tile
+        }
+        mbar_wait(&sm.bar, it & 1u);
+
+        // ---- pass A: classify the warp's rows ------------------------------------------------------------
+        int n_att = 0, n_diff = 0;
+#pragma unroll 1
+        for (int r = 0; r < DN_WROWS; ++r) {
+            const int row = wid * DN_WROWS + r, li = row >> 3, lj = row & 7;
+            const int p = p0 + li, j = j0 + lj, k = k0 + lane;
+            const bool active = p < a.p_hi && j < L && k < L;
+            const int rowbase = (li + 2) * TL_HJ + lj + 2;
+            const uint32_t vaddr = vx0 + (uint32_t)(rowbase * TL_VK + TL_VK0 + lane);
+            const unsigned c = lds_u8<0>(vaddr);
+            const uint32_t wlo = dn_pack(vaddr, 0, std::integer_sequence<int, 0, 1, 2, 3, 4, 5, 6, 7>{});
+            const uint32_t whi = dn_pack(vaddr, 8, std::integer_sequence<int, 8, 9, 10, 11, 12, 13>{});
+            const unsigned code = c & 15u;
+            const bool is_emp = active && code == TC_EMPTY;
+            const bool is_occ = active && (code & 1u) && code != TC_DEFECT;
+            const uint32_t att = (wlo & (wlo >> 3) & 0x11111111u) | (whi & (whi >> 3) & 0x00111111u);
+            const uint32_t emp = (~wlo & (wlo >> 3) & 0x11111111u) | (~whi & (whi >> 3) & 0x00111111u);
+            const bool to_diff = is_occ && emp != 0u;
+            const int s = (p * L + j) * L + k;
+            const uint64_t w = (uint64_t)wlo | ((uint64_t)whi << 32);
+            // pairless empty sites: nucleation only.  Where they are most of the row they are evaluated here.
+            const bool lone = is_emp && att == 0u;
+            const bool inl = __popc(__ballot_sync(0xffffffffu, lone)) >= DN_INLINE_MIN;
+            double T_self = 1.0;
+            if (is_emp && (inl || p == a.top_plane)) T_self = lds_f64(po0 + (uint32_t)((rowbase * TL_PK + TL_PK0 + lane) * 8));
+            const bool to_att = is_emp && !(lone && inl);
+            if (active && !to_att && !to_diff) {
+                double sum = 0.0;
+                if (lone) {
+                    const double local_T = pymax(T_self, 1.0);
+                    sum = tile_nuc_rate(P, sm.tab, w, 0ull, local_T, rcp(P.kT * local_T));
+                }
+                a.site_rate[s] = sum;
+            }
+            if (p == a.top_plane && active) {                            // deposition (:55-72): top plane only
+                double dep;
+                a.dep_rate[j * L + k] = (is_emp && dep_rate(P, T_self, &dep)) ? dep : NAN;
+            }
+            const unsigned b_att = __ballot_sync(0xffffffffu, to_att), b_diff = __ballot_sync(0xffffffffu, to_diff);
+            const uint32_t ent = (uint32_t)(li << 8 | lj << 5 | lane) | (c << 16);
+            if (to_att) {
+                const int pos = n_att + __popc(b_att & lt_mask);
+                wl.w[pos] = w; wl.e[pos] = ent;
+            }
+            if (to_diff) {
+                const int pos = DN_LIST - 1 - n_diff - __popc(b_diff & lt_mask);
+                wl.w[pos] = w; wl.e[pos] = ent;
+            }
+            n_att += __popc(b_att); n_diff += __popc(b_diff);
+        }
+        __syncwarp();
+
+        // ---- pass B: empty sites (nucleation + attachment, kmc_event_rates.py:116-158) --------------------
+#pragma unroll 1
+        for (int b0 = 0; b0 < n_att; b0 += 32) {
+            if (b0 + lane < n_att) {
+                const uint64_t w = wl.w[b0 + lane];
+                const uint32_t e = wl.e[b0 + lane];
+                const int li = (e >> 8) & 3, lj = (e >> 5) & 7, lk = e & 31;
+                const int rowbase = (li + 2) * TL_HJ + lj + 2;
+                const uint32_t base = po0 + (uint32_t)((rowbase * TL_PK + TL_PK0 + lk) * 8);
+                const int k = k0 + lk;
+                const int s = ((p0 + li) * L + j0 + lj) * L + k;
+                const double T_self = lds_f64(base);                     // an empty site's pairop is its temperature
+                double T_m = T_self, T_p = T_self;
+                if ((uint32_t)w & 0x11111111u || (uint32_t)(w >> 32) & 0x00111111u) {     // an occupied neighbour: grad_z (:151-153)
+                    const uint32_t vaddr = vx0 + (uint32_t)(rowbase * TL_VK + TL_VK0 + lk);
+                    // an empty k neighbour keeps its temperature in pairop
+                    if (k > 0) T_m = (lds_u8<-1>(vaddr) & 15u) == TC_EMPTY ? lds_f64(base - 8u) : a.T[s - 1];
+                    if (k < L - 1) T_p = (lds_u8<1>(vaddr) & 15u) == TC_EMPTY ? lds_f64(base + 8u) : a.T[s + 1];
+                }
+                const TilePrep q = tile_prep_emp(P, sm.tab, w, T_self, T_m, T_p);
+                a.site_rate[s] = q.pm ? dn_pairs<true, ILP>(P, sm, pair_walk_mask(q.pm), base, dpb0, q.A, q.B, q.sum0) : q.sum0;
+            }
+        }
+        // ---- pass B: occupied sites (diffusion, :79-109) --------------------------------------------------
+#pragma unroll 1
+        for (int b0 = 0; b0 < n_diff; b0 += 32) {
+            if (b0 + lane < n_diff) {
+                const uint64_t w = wl.w[DN_LIST - 1 - b0 - lane];
+                const uint32_t e = wl.e[DN_LIST - 1 - b0 - lane];
+                const int li = (e >> 8) & 3, lj = (e >> 5) & 7, lk = e & 31;
+                const unsigned c = e >> 16;
+                const int rowbase = (li + 2) * TL_HJ + lj + 2;
+                const uint32_t base = po0 + (uint32_t)((rowbase * TL_PK + TL_PK0 + lk) * 8);
+                const int s = ((p0 + li) * L + j0 + lj) * L + k0 + lk;
+                const TilePrep q = tile_prep_occ(P, sm.tab, w, c & 15u, (int)(c >> 4), a.T[s]);
+                a.site_rate[s] = dn_pairs<false, ILP>(P, sm, pair_walk_mask(q.pm), base, dpb0, q.A, q.B, 0.0);
+            }
+        }
+        __syncthreads();                                           // the tile and the lists may be overwritten
+    }
+}
+
+template <int ILP>
+static int dense_launch(cet_ctx *c, const DenseArgs &a, int *blocks_per_sm)
+{
+    const size_t smem = sizeof(DenseSmem) + 1024;
+    if (*blocks_per_sm == 0) {
+        CET_CUDA(cudaFuncSetAttribute(rates_dense_kernel<ILP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rates_dense_kernel<ILP>, TL_THREADS, smem));
+        CET_REQUIRE(nb >= 1, "rates_dense_kernel does not fit an SM");
+        *blocks_per_sm = nb;
+    }
+    const int grid = std::min(a.n_tiles, sm_count(c) * *blocks_per_sm);
+    rates_dense_kernel<ILP><<<grid, TL_THREADS, smem, c->stream>>>(a, *(const CUtensorMap *)c->tmap_vox, *(const CUtensorMap *)c->tmap_po);
+    CET_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Dense evaluation of local planes [p_lo, p_hi) from cvox / pairop (rows a tensor map can describe: tile_tma_ok).
+int rates_rows_dense(cet_ctx *c, int p_lo, int p_hi)
+{
+    if (p_hi <= p_lo) return 0;
+    if (int rc = rate_tables_ensure(c)) return rc;
+    if (int rc = tile_maps_ensure(c)) return rc;
+    DenseArgs a;
+    memset(&a, 0, sizeof(a));
+    a.T = c->T; a.site_rate = c->site_rate; a.dep_rate = c->dep_rate; a.tab = c->rate_tab;
+    a.queue = (unsigned int *)(c->rate_tab + RT_TABLE_DOUBLES) + 2;
+    a.P = c->rp;
+    a.L = (int)c->n1; a.p_lo = p_lo; a.p_hi = p_hi;
+    const int top = (int)(c->n0 - 1 - (c->i_begin - c->halo));
+    a.top_plane = (top >= p_lo && top < p_hi) ? top : -1;
+    a.njb = (int)((c->n1 + TL_J - 1) / TL_J); a.nkb = (int)((c->n2 + TL_K - 1) / TL_K);
+    a.n_tiles = ((p_hi - p_lo + TL_I - 1) / TL_I) * a.njb * a.nkb;
+    CET_CUDA(cudaMemsetAsync(a.queue, 0, sizeof(unsigned int), c->stream));
+    // pairs in flight per lane and trip: 2 (default) or 1 (debug flag 131072); the same bits either way
+    if (c->debug_flags & 131072) { if (int rc = dense_launch<1>(c, a, &c->dense_blocks[0])) return rc; }
+    else if (int rc = dense_launch<2>(c, a, &c->dense_blocks[1])) return rc;
+    CET_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace cet

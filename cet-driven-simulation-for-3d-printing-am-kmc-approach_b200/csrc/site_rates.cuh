@@ -76,13 +76,11 @@ static __constant__ double c_exp_k[9] = {0x1.71547652b82fep+5, 6755399441055744.
                                          0x1.6c16c16c16c17p-10, 0x1.1111111111111p-7, 0x1.5555555555555p-5,
                                          0x1.5555555555555p-3, 0.5};
 #endif
-CET_HD double fast_exp_t(double x, const double *tab)      // tab: 2^(j/32), j = 0..31 (any address space)
+// the in-range part of fast_exp_t (|x| < 700)
+CET_HD double fast_exp_core(double x, const double *tab)   // tab: 2^(j/32), j = 0..31 (any address space)
 {
-    if (!(fabs(x) < 700.0)) return slow_exp(x);
-    const double big = 6755399441055744.0;                                  // 1.5 * 2^52: rint by magic add
-    (void)big;
 #if defined(__CUDA_ARCH__)
-    const double tt = __fma_rn(x, c_exp_k[0], c_exp_k[1]);                 // x * 32/ln2
+    const double tt = __fma_rn(x, c_exp_k[0], c_exp_k[1]);                 // x * 32/ln2, rint by magic add (1.5 * 2^52)
     const int n = __double2loint(tt);
     const double nf = tt - c_exp_k[1];
     double r = __fma_rn(nf, c_exp_k[2], x);                                 // ln2/32 in two parts
@@ -96,6 +94,7 @@ CET_HD double fast_exp_t(double x, const double *tab)      // tab: 2^(j/32), j =
     const double y = __fma_rn(t, p, t);
     return __hiloint2double(__double2hiint(y) + ((n >> 5) << 20), __double2loint(y));
 #else
+    const double big = 6755399441055744.0;
     const double tt = fma(x, 0x1.71547652b82fep+5, big);
     int64_t bits;
     memcpy(&bits, &tt, 8);
@@ -117,6 +116,11 @@ CET_HD double fast_exp_t(double x, const double *tab)      // tab: 2^(j/32), j =
     memcpy(&out, &yb, 8);
     return out;
 #endif
+}
+CET_HD double fast_exp_t(double x, const double *tab)
+{
+    if (!(fabs(x) < 700.0)) return slow_exp(x);
+    return fast_exp_core(x, tab);
 }
 
 #if defined(__CUDA_ARCH__)

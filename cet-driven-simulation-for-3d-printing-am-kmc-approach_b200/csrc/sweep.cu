@@ -54,6 +54,7 @@ bool tile_tma_ok(const cet_ctx *c);
 int stamp_fill(cet_ctx *c, int p_lo, int p_hi);
 int rates_rows_dirty_compact(cet_ctx *c, int p_lo, int p_hi, const uint32_t *stamp, int32_t *list, unsigned int *counter);
 int rates_rows_compact(cet_ctx *c, int p_lo, int p_hi);
+int rates_rows_dense(cet_ctx *c, int p_lo, int p_hi);                            // rates_dense.cu
 int rate_tables_ensure(cet_ctx *c);
 
 struct Record {          // one fired event
@@ -715,10 +716,12 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
     if (!c->sweep_rates_valid) {                     // new lattice, new T or new parameters: dense rebuild
         if (tiled && !(c->debug_flags & 8)) {
             ProfScope ps(c, PROF_RATES);
-            // dense rebuild: the TMA-staged tile kernel where the rows allow TMA (5.7 ms at 512^3 against 6.1 ms for
-            // the dense gather kernel on the compact state, which serves every other L; flag 65536 forces the latter)
-            const bool by_tiles = (c->debug_flags & 32) || (tile_tma_ok(c) && !(c->debug_flags & 65536));
-            if (by_tiles) { if (int rc = tile_pass(c, R.eval_lo, R.eval_hi, true)) return rc; }
+            // dense rebuild: the class-sorted TMA tile kernel (rates_dense.cu) where the rows allow TMA; the dense
+            // gather kernel on the compact state serves every other L (flag 65536 forces it), and flag 32 runs the
+            // refresh's tile kernel over every site instead (the three agree bit for bit)
+            const bool tma = tile_tma_ok(c) && !(c->debug_flags & 65536);
+            if (c->debug_flags & 32) { if (int rc = tile_pass(c, R.eval_lo, R.eval_hi, true)) return rc; }
+            else if (tma) { if (int rc = rates_rows_dense(c, R.eval_lo, R.eval_hi)) return rc; }
             else if (int rc = rates_rows_compact(c, R.eval_lo, R.eval_hi)) return rc;
         } else {
             if (tiled) c->nst_valid = false;         // nobody maintains the neighbour cache on the tile path

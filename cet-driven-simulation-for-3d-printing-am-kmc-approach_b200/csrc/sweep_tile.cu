@@ -21,6 +21,7 @@
 #include "ctx.cuh"
 #include "reduce.cuh"
 #include "tile_state.cuh"
+#include "tma.cuh"
 
 namespace cet {
 
@@ -63,39 +64,6 @@ struct TileArgs {
     int njb, nkb, n_tiles;
     int mode;
 };
-
-// ---- mbarrier / TMA (PTX ISA 8.x; sm_90+) ------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "TL_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra TL_DONE;\n"
-        "bra TL_WAIT;\n"
-        "TL_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1, int c2)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
 
 // What a lane knows about its site before the pair phase.
 struct TileSite {
@@ -557,7 +525,7 @@ static EncodeTiledFn encode_tiled_fn()
 
 
 // Tensor maps over the local arrays (k fastest, then j, then plane); rebuilt when a pointer changed.
-static int tile_maps_ensure(cet_ctx *c)
+int tile_maps_ensure(cet_ctx *c)
 {
     if (c->tmap_vox_ptr == c->cvox && c->tmap_po_ptr == c->pairop) return 0;
     EncodeTiledFn enc = encode_tiled_fn();

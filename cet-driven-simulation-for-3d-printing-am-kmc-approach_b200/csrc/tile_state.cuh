@@ -70,38 +70,51 @@ struct TilePrep {
     double sum0;        // nucleation rate (0 when there is none)
     bool is_emp;
 };
+// The halves of tile_site_prep by site class: the dense kernel (rates_dense.cu) sorts the sites of a tile by
+// class first and calls them separately; tile_site_prep composes the same functions, so both give the same bits.
+CET_HD int tile_n_in(uint64_t w) { return popc64((w | (w >> 3)) & CET_NIB_LSB); }     // a class code is non-zero iff bit 0 or bit 3 is set
+// nucleation rate of an empty site (kmc_event_rates.py:120-131); 0 when the event does not exist
+CET_HD double tile_nuc_rate(const cet_rate_params &P, const double *tab, uint64_t w, uint64_t m_att, double local_T, double inv_kTT)
+{
+    if (!nuc_exists(P, local_T)) return 0.0;
+    const int n_imp = popc64((w >> 1) & m_att) + popc64((w >> 2) & m_att);
+    return nuc_from_exp(P, fast_exp_t(nuc_exp_arg(P, local_T, tab[RT_KEFF + n_imp * 16 + tile_n_in(w)], inv_kTT), tab + RT_EXP2));
+}
+CET_HD TilePrep tile_prep_emp(const cet_rate_params &P, const double *tab, uint64_t w, double T_self, double T_km, double T_kp)
+{
+    TilePrep r;
+    r.is_emp = true; r.A = 0.0; r.B = 0.0;
+    const uint64_t m_att = w & (w >> 3) & CET_NIB_LSB;             // occupied neighbours of an attachable species
+    const double local_T = pymax(T_self, 1.0);
+    const double inv_kTT = rcp(P.kT * local_T);
+    r.pm = m_att;
+    r.sum0 = tile_nuc_rate(P, tab, w, m_att, local_T, inv_kTT);
+    if (r.pm) { r.A = inv_kTT; r.B = emp_ng(P, local_T, T_km, T_kp); }
+    return r;
+}
+// code: TC_W / TC_RE / TC_C; df: the site's defects_mask value
+CET_HD TilePrep tile_prep_occ(const cet_rate_params &P, const double *tab, uint64_t w, unsigned code, int df, double T_self)
+{
+    TilePrep r;
+    r.is_emp = false; r.A = 0.0; r.B = 0.0; r.sum0 = 0.0;
+    r.pm = ~w & (w >> 3) & CET_NIB_LSB;                            // empty neighbours inside the lattice
+    if (r.pm) {
+        const double local_T = pymax(T_self, 1.0);
+        const double inv_kTT = rcp(P.kT * local_T);
+        const int sp = code == TC_W ? 0 : code == TC_RE ? 1 : 2;                           // :83-91
+        const double e = fast_exp_t(occ_exp_arg(df, tab[RT_ETOT + sp * 16 + popc64(w & CET_NIB_LSB)], inv_kTT), tab + RT_EXP2);
+        r.A = local_T; r.B = P.nu * e;
+    }
+    return r;
+}
 CET_HD TilePrep tile_site_prep(const cet_rate_params &P, const double *tab, uint64_t w, unsigned c, double T_self,
                                double T_km, double T_kp)
 {
-    TilePrep r;
-    r.pm = 0; r.A = 0.0; r.B = 0.0; r.sum0 = 0.0;
     const unsigned code = c & 15u;
-    const int df = (int)(c >> 4);
-    r.is_emp = code == TC_EMPTY;
-    const bool is_occ = (code & 1u) && code != TC_DEFECT;
-    if (!r.is_emp && !is_occ) return r;
-    const uint64_t w3 = w >> 3;
-    const uint64_t m_occ = w & CET_NIB_LSB;                        // occupied neighbours
-    const uint64_t m_att = w & w3 & CET_NIB_LSB;                   // ... of an attachable species
-    const uint64_t m_emp = ~w & w3 & CET_NIB_LSB;                  // empty neighbours inside the lattice
-    const double local_T = pymax(T_self, 1.0);
-    const double inv_kTT = rcp(P.kT * local_T);
-    if (is_occ) {
-        r.pm = m_emp;
-        if (r.pm) {
-            const int sp = code == TC_W ? 0 : code == TC_RE ? 1 : 2;                       // :83-91
-            const double e = fast_exp_t(occ_exp_arg(df, tab[RT_ETOT + sp * 16 + popc64(m_occ)], inv_kTT), tab + RT_EXP2);
-            r.A = local_T; r.B = P.nu * e;
-        }
-        return r;
-    }
-    r.pm = m_att;
-    if (nuc_exists(P, local_T)) {
-        const int n_imp = popc64((w >> 1) & m_att) + popc64((w >> 2) & m_att);
-        const int n_in = popc64(nib_nonzero(w));
-        r.sum0 = nuc_from_exp(P, fast_exp_t(nuc_exp_arg(P, local_T, tab[RT_KEFF + n_imp * 16 + n_in], inv_kTT), tab + RT_EXP2));
-    }
-    if (r.pm) { r.A = inv_kTT; r.B = emp_ng(P, local_T, T_km, T_kp); }
+    if (code == TC_EMPTY) return tile_prep_emp(P, tab, w, T_self, T_km, T_kp);
+    if ((code & 1u) && code != TC_DEFECT) return tile_prep_occ(P, tab, w, code, (int)(c >> 4), T_self);
+    TilePrep r;
+    r.pm = 0; r.A = 0.0; r.B = 0.0; r.sum0 = 0.0; r.is_emp = false;
     return r;
 }
 // one pair: op = pairop of the neighbour

@@ -1,8 +1,9 @@
 """GPU: synchronous-sublattice sweeps (csrc/sweep.cu, csrc/sweep_tile.cu) — invariants, determinism
 and level-3 parity (trajectory observables against the serial oracle within statistical bounds).
 Rate-maintenance variants (Context.debug_flags): COMPACT (default) = stamped sites refreshed by list-driven
-gathers from the compact tile state, dense rebuilds by the TMA-staged tile kernel when L % 16 == 0; TILE = the
-tile kernel for the refresh too (TMA staging), VECTOR / SCALAR its other staging modes, SERIAL its per-lane pair
+gathers from the compact tile state, dense rebuilds by the class-sorted TMA tile kernel (rates_dense.cu) when
+L % 16 == 0 (DENSE_ILP1: one pair in flight per lane instead of two); TILE = the refresh's tile kernel for the
+refresh and the rebuild (TMA staging), VECTOR / SCALAR its other staging modes, SERIAL its per-lane pair
 loop; DENSE_COMPACT = dense rebuilds by the compact gather kernel; GATHER = refresh + rebuild of the first design
 (neighbour-class cache + unit vectors)."""
 import numpy as np
@@ -18,7 +19,7 @@ def _sweep_params(cet, seed, L, eps=0.02, p_max=0.25, defect_fraction=0.0, therm
     return sp
 
 
-COMPACT, GATHER, TILE, DENSE_COMPACT = 0, 2, 32, 65536
+COMPACT, GATHER, TILE, DENSE_COMPACT, DENSE_ILP1 = 0, 2, 32, 65536, 131072
 SCALAR, SERIAL, VECTOR = TILE | 1, TILE | 4, TILE | 16
 TMA = TILE
 FUSED = COMPACT
@@ -93,7 +94,7 @@ def test_refresh_variants_agree(cet, L):
     and resident rates."""
     from cetkmc._config import thermal_params
     outs = []
-    for flags in (COMPACT, DENSE_COMPACT, TILE, SCALAR, VECTOR, SERIAL, SERIAL | 16, GATHER, COMPACT | 8):
+    for flags in (COMPACT, DENSE_ILP1, DENSE_COMPACT, TILE, SCALAR, VECTOR, SERIAL, SERIAL | 16, GATHER, COMPACT | 8):
         ctx, st, th, ph, T, df = _setup(cet, L, flags=flags)
         res = ctx.sweep_run(7, _sweep_params(cet, 5, L, eps=0.01, p_max=0.2, defect_fraction=0.01, thermal_every=3),
                             thermal_params(1e-6, nan_to_num=True))
@@ -295,3 +296,39 @@ def test_resident_rates_equal_rebuild_after_sweeps(cet, L, flags):
     ctx.close()
     np.testing.assert_array_equal(sr1, sr2)
     np.testing.assert_array_equal(dr1, dr2)
+
+
+@pytest.mark.parametrize("L,flags", [(64, COMPACT), (80, COMPACT), (80, DENSE_ILP1), (96, DENSE_COMPACT)])
+def test_dense_rebuild_edge_cases(cet, oracle, L, flags):
+    """The dense rebuild kernels on inputs that leave fast_exp's range and exercise every clamp: cold blocks
+    (T below 1 K and a few kelvin: Arrhenius arguments far beyond -700, the out-of-line path), sites at and
+    above T_melt (no nucleation; the max(T_melt - T, 1) clamps), a steep temperature step along k (grad_z),
+    partial tiles at the lattice faces (L = 80), the top plane's deposition rates.  The sweep's resident rates
+    after a rebuild with (practically) no event must equal the per-event gather kernel bit for bit and the
+    oracle within 1e-12."""
+    from cetkmc import _synth
+    from cetkmc._config import rate_params
+    packed, th, ph, T = _synth.half_grown(L, seed=9, grain=4)
+    T = T.copy()
+    T[3:9, 5:20, 10:30] = 0.25
+    T[20:26, :, 4:12] = 7.0
+    T[30:40, 10:30, :] = 3695.0
+    T[41:44, :, L // 2 - 3:] = 3900.0
+    T[50:60, 20:40, L // 2:] += 600.0
+    T[L - 1, 0:8, 0:8] = 0.5
+    ctx = cet.Context(L=L)
+    ctx.debug_flags(flags)
+    ctx.set_rate_params(rate_params(0.1))
+    st, df = _synth.unpack(packed)
+    ctx.upload(state=st, theta=th, phi=ph, T=T, defects=df)
+    res = ctx.sweep_run(1, _sweep_params(cet, 3, L, eps=1e-12, p_max=1e-9), None)
+    assert res["events_applied"] == 0
+    sr1, dr1 = ctx.rates_download()
+    ctx.rates_build()
+    sr2, dr2 = ctx.rates_download()
+    ctx.close()
+    np.testing.assert_array_equal(sr1, sr2)
+    np.testing.assert_array_equal(dr1, dr2)
+    o_sr, o_dep, _, _ = oracle.site_rates(st, th, ph, T, df, L, oracle.make_params(0.1))
+    np.testing.assert_allclose(sr1, o_sr, rtol=1e-12, atol=0.0)
+    np.testing.assert_allclose(dr1, o_dep, rtol=1e-12, atol=0.0, equal_nan=True)
