@@ -2,6 +2,7 @@
 // error plumbing shared by all translation units.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -46,16 +47,26 @@ struct DeltaEntry {
 constexpr int DELTA_ZONE = 6;      // planes per face a neighbour keeps as ghosts (= SWEEP_HALO)
 constexpr int DELTA_HEADER = 16;   // bytes in front of the entries; the first 4 hold the count
 
+// Three 128-byte lines, by who touches them while a kernel runs: a read of a line that thousands of atomics
+// are queued on waits behind them, and every CTA of the sweep kernels starts by reading tau or n_fired.
 struct SweepState {
-    unsigned long long n_fired_total, n_applied, n_nuc;   // running totals over owned sites (device atomics)
+    // line 0 — running totals over owned sites, advanced by device atomics at the end of the apply CTAs
+    unsigned long long n_fired_total, n_applied, n_nuc;
     unsigned long long n_refreshed_total;                 // sites re-evaluated by the neighbour-rate refresh
+    unsigned long long pad_line0_[12];
+    // line 1 — list reservations (atomics of the stream / scan kernels), read by the kernels that follow
     unsigned int n_fired;                           // fired-site list length of the current sweep
     unsigned int n_dirty, n_dirty_emp;              // refresh list length (one mixed list; n_dirty_emp stays 0, kept for the layout)
     unsigned int overflow, dirty_overflow, pad0_;   // the fired list overflowed (events dropped)
+    unsigned int pad_line1_[26];
+    // line 2 — written by the single-CTA finalize kernel only
     double sum_rate, max_rate;                      // totals of the rates seen by the last sweep
     double tau, time;                               // interval of the next sweep; accumulated time
     int32_t terminated, pad_;
+    unsigned long long pad_line2_[11];
 };
+static_assert(offsetof(SweepState, n_fired) == 128 && offsetof(SweepState, sum_rate) == 256 && sizeof(SweepState) == 384,
+              "SweepState: one 128-byte line per access class");
 
 }  // namespace cet
 

@@ -26,6 +26,7 @@
 #include "ctx.cuh"
 #include "tile_state.cuh"
 #include "tma.cuh"
+#include "pair_walk.cuh"
 
 namespace cet {
 
@@ -34,22 +35,21 @@ int tile_maps_ensure(cet_ctx *c);        // sweep_tile.cu
 int sm_count(cet_ctx *c);
 
 constexpr int DN_ROWS = TL_I * TL_J;                     // 32 rows of 32 sites per tile
-constexpr int DN_WROWS = DN_ROWS / TL_WARPS;             // rows per warp
-constexpr int DN_LIST = DN_WROWS * 32;                   // list slots per warp: every site is in at most one list
+constexpr int DN_WROWS = DN_ROWS / TL_WARPS;             // rows per warp in pass A
 constexpr int DN_INLINE_MIN = 12;                        // pass A evaluates pairless empty sites itself from this many per row on
 
-struct DenseWarpList {
-    uint64_t w[DN_LIST];                                 // class codes of the 14 neighbours, 4 bits per slot
-    uint32_t e[DN_LIST];                                 // tile-local site index (li << 8 | lj << 5 | lk) | own cvox byte << 16
-};
 struct DenseSmem {
     double po[TL_HI * TL_HJ * TL_PK];                    // 128-byte aligned TMA destinations first
     uint8_t vx[TL_VBYTES];
     double tab[RT_TABLE_DOUBLES];
-    DenseWarpList wl[TL_WARPS];
+    // the tile's two site lists, shared by the CTA (every site is in at most one): empty sites from the front,
+    // occupied sites from the back
+    uint64_t lw[TL_SITES];                               // class codes of the 14 neighbours, 4 bits per slot
+    uint32_t le[TL_SITES];                               // tile-local site index (li << 8 | lj << 5 | lk) | own cvox byte << 16
     int16_t dpb[16];                                     // [15 - o]: byte offset of neighbour slot o's pairop from the site's own
     unsigned long long bar;
-    int tile[2];                                         // tile index of this / the next iteration (popped ahead of need)
+    int4 tile[2];                                        // {tile index, p0, j0, k0} of this / the next iteration (popped ahead of need)
+    int n_list[2][2];                                    // [tile parity][att, diff] list lengths
 };
 
 struct DenseArgs {
@@ -62,19 +62,6 @@ struct DenseArgs {
     int njb, nkb, n_tiles;
 };
 
-template <int OFF>
-__device__ __forceinline__ unsigned lds_u8(uint32_t addr)
-{
-    unsigned v;
-    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
-    return v;
-}
-__device__ __forceinline__ double lds_f64(uint32_t addr)
-{
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-    return v;
-}
 template <int O>
 __device__ __forceinline__ unsigned dn_code(uint32_t vaddr)
 {
@@ -85,40 +72,6 @@ __device__ __forceinline__ uint32_t dn_pack(uint32_t vaddr, int base, std::integ
 {
     return ((dn_code<O>(vaddr) << (4 * (O - base))) + ...);            // disjoint nibbles: + is |, and one LEA per slot
 }
-__device__ __forceinline__ int lds_s16(uint32_t addr)
-{
-    int v;
-    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-// bits 4*o of a nibble mask -> bits 2*o
-__device__ __forceinline__ uint32_t nib_compress2(uint32_t x)
-{
-    x = (x | (x >> 2)) & 0x05050505u;
-    x = (x | (x >> 4)) & 0x00550055u;
-    return (x | (x >> 8)) & 0x5555u;
-}
-// Walk order of a site's pair mask: slot o at bit 30 - 2*o, so the leading set bit is the lowest slot and its
-// position is the BYTE offset of the slot's entry in the reversed 16-bit offset table (DenseSmem::dpb).
-__device__ __forceinline__ uint32_t pair_walk_mask(uint64_t pm)
-{
-    return __brev((nib_compress2((uint32_t)pm) | (nib_compress2((uint32_t)(pm >> 32)) << 16)) << 1);
-}
-
-// `sum += keep_rate(P, rate)` without the selects: rates are never negative and sum never -0 or NaN, so adding the
-// kept rate or nothing gives the same bits; for rate > threshold, `rate < inf` is a test of the high word.
-__device__ __forceinline__ void add_kept(const cet_rate_params &P, double &sum, double rate)
-{
-    asm("{\n"
-        ".reg .pred p;\n"
-        "setp.gt.f64 p, %1, %2;\n"
-        "setp.lt.and.s32 p, %3, 0x7ff00000, p;\n"
-        "@p add.rn.f64 %0, %0, %1;\n"
-        "}\n"
-        : "+d"(sum)
-        : "d"(rate), "d"(P.rate_threshold), "r"(__double2hiint(rate)));
-}
-
 // The pairs of one site in slot order, out of line: the rare sites with an Arrhenius argument outside fast_exp's range.
 template <bool ATT>
 __device__ __noinline__ double dn_pairs_slow(const cet_rate_params &P, const double *tab, const int16_t *dpb, uint32_t m, uint32_t base, double A,
@@ -152,22 +105,13 @@ __device__ __forceinline__ double dn_pairs(const cet_rate_params &P, const Dense
             m &= (1u << h) - 1u;
             double op = 0.0;
             if (on[u]) op = lds_f64(base + (uint32_t)lds_s16(dpb + (uint32_t)h));
-            if (ATT) {                                                   // att_pair_rate_E (kmc_event_rates.py:147-157)
-                const double x = -op * A;
-                xmax = max(xmax, __double2hiint(x) & 0x7fffffff);
-                rate[u] = fast_exp_core(x, sm.tab + RT_EXP2) * B;
-            } else {                                                     // diff_pair_rate (:102-108)
-                const double neighbor_T = pymax(op, 1.0);
-                const double dT = fabs(A - neighbor_T);
-                const double denom = pymax(P.T_melt - neighbor_T, 1.0);
-                rate[u] = fma(0.1 * dT, rcp1(denom), 1.0) * B;
-            }
+            rate[u] = pair_rate_raw<ATT>(P, sm.tab + RT_EXP2, op, A, B, xmax);
         }
 #pragma unroll
         for (int u = 0; u < ILP; ++u)
             if (on[u]) add_kept(P, sum, rate[u]);
     } while (m);
-    const bool bad = xmax >= 0x4085e000;                                 // !(|x| < 700) for some pair, NaN included: fast_exp's range
+    const bool bad = xmax >= EXP_RANGE_HI;                               // outside fast_exp's range
     if (ATT && bad) sum = dn_pairs_slow<ATT>(P, sm.tab + RT_EXP2, sm.dpb, m0, base, A, B, sum0);
     return sum;
 }
@@ -185,31 +129,37 @@ __global__ void __launch_bounds__(TL_THREADS, 4)
 
     for (int q = tid; q < RT_TABLE_DOUBLES; q += TL_THREADS) sm.tab[q] = a.tab[q];
     if (tid < 14) sm.dpb[15 - tid] = (int16_t)((((int)c_nb_off[tid][0] * TL_HJ + c_nb_off[tid][1]) * TL_PK + c_nb_off[tid][2]) * 8);
+    const int tiles_per_iblock = a.njb * a.nkb;
+    // thread 0 pops a tile and works out its origin for everybody
+    auto pop_tile = [&](int slot) {
+        const int t = (int)atomicAdd(a.queue, 1u);
+        const int ib = t / tiles_per_iblock, r = t - ib * tiles_per_iblock, jb = r / a.nkb, kb = r - jb * a.nkb;
+        sm.tile[slot] = make_int4(t, a.p_lo + TL_I * ib, TL_J * jb, TL_K * kb);
+    };
     if (tid == 0) {
         mbar_init(&sm.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        sm.tile[0] = (int)atomicAdd(a.queue, 1u);
+        pop_tile(0);
+        sm.n_list[0][0] = 0; sm.n_list[0][1] = 0;
     }
     __syncthreads();
-    DenseWarpList &wl = sm.wl[wid];
     const uint32_t vx0 = smem_u32(sm.vx), po0 = smem_u32(sm.po), dpb0 = smem_u32(sm.dpb);
-    const int tiles_per_iblock = a.njb * a.nkb;
 
     for (unsigned it = 0;; ++it) {
-        const int t = sm.tile[it & 1u];
-        if (t >= a.n_tiles) break;
-        const int kb = t % a.nkb, jb = (t / a.nkb) % a.njb, ib = t / tiles_per_iblock;
-        const int p0 = a.p_lo + TL_I * ib, j0 = TL_J * jb, k0 = TL_K * kb;
+        const int4 ti = sm.tile[it & 1u];
+        if (ti.x >= a.n_tiles) break;
+        const int p0 = ti.y, j0 = ti.z, k0 = ti.w;
+        int *n_list = sm.n_list[it & 1u];
         if (tid == 0) {
             mbar_expect_tx(&sm.bar, (unsigned)(TL_VBYTES + TL_PBYTES));
             tma_load_3d(sm.vx, &tm_vox, &sm.bar, k0 - TL_VK0, j0 - 2, p0 - 2);
             tma_load_3d(sm.po, &tm_po, &sm.bar, k0 - TL_PK0, j0 - 2, p0 - 2);
-            sm.tile[(it + 1u) & 1u] = (int)atomicAdd(a.queue, 1u);       // read after the barrier that ends this tile
+            pop_tile((it + 1u) & 1u);                                    // read after the barrier that ends this tile
+            sm.n_list[(it + 1u) & 1u][0] = 0; sm.n_list[(it + 1u) & 1u][1] = 0;
         }
         mbar_wait(&sm.bar, it & 1u);
 
         // ---- pass A: classify the warp's rows ------------------------------------------------------------
-        int n_att = 0, n_diff = 0;
 #pragma unroll 1
         for (int r = 0; r < DN_WROWS; ++r) {
             const int row = wid * DN_WROWS + r, li = row >> 3, lj = row & 7;
@@ -247,55 +197,65 @@ __global__ void __launch_bounds__(TL_THREADS, 4)
                 a.dep_rate[j * L + k] = (is_emp && dep_rate(P, T_self, &dep)) ? dep : NAN;
             }
             const unsigned b_att = __ballot_sync(0xffffffffu, to_att), b_diff = __ballot_sync(0xffffffffu, to_diff);
-            const uint32_t ent = (uint32_t)(li << 8 | lj << 5 | lane) | (c << 16);
-            if (to_att) {
-                const int pos = n_att + __popc(b_att & lt_mask);
-                wl.w[pos] = w; wl.e[pos] = ent;
-            }
-            if (to_diff) {
-                const int pos = DN_LIST - 1 - n_diff - __popc(b_diff & lt_mask);
-                wl.w[pos] = w; wl.e[pos] = ent;
-            }
-            n_att += __popc(b_att); n_diff += __popc(b_diff);
-        }
-        __syncwarp();
-
-        // ---- pass B: empty sites (nucleation + attachment, kmc_event_rates.py:116-158) --------------------
-#pragma unroll 1
-        for (int b0 = 0; b0 < n_att; b0 += 32) {
-            if (b0 + lane < n_att) {
-                const uint64_t w = wl.w[b0 + lane];
-                const uint32_t e = wl.e[b0 + lane];
-                const int li = (e >> 8) & 3, lj = (e >> 5) & 7, lk = e & 31;
-                const int rowbase = (li + 2) * TL_HJ + lj + 2;
-                const uint32_t base = po0 + (uint32_t)((rowbase * TL_PK + TL_PK0 + lk) * 8);
-                const int k = k0 + lk;
-                const int s = ((p0 + li) * L + j0 + lj) * L + k;
-                const double T_self = lds_f64(base);                     // an empty site's pairop is its temperature
-                double T_m = T_self, T_p = T_self;
-                if ((uint32_t)w & 0x11111111u || (uint32_t)(w >> 32) & 0x00111111u) {     // an occupied neighbour: grad_z (:151-153)
-                    const uint32_t vaddr = vx0 + (uint32_t)(rowbase * TL_VK + TL_VK0 + lk);
-                    // an empty k neighbour keeps its temperature in pairop
-                    if (k > 0) T_m = (lds_u8<-1>(vaddr) & 15u) == TC_EMPTY ? lds_f64(base - 8u) : a.T[s - 1];
-                    if (k < L - 1) T_p = (lds_u8<1>(vaddr) & 15u) == TC_EMPTY ? lds_f64(base + 8u) : a.T[s + 1];
+            if (b_att | b_diff) {
+                int base_a = 0, base_d = 0;
+                if (lane == 0) {
+                    if (b_att) base_a = atomicAdd(&n_list[0], __popc(b_att));
+                    if (b_diff) base_d = atomicAdd(&n_list[1], __popc(b_diff));
                 }
-                const TilePrep q = tile_prep_emp(P, sm.tab, w, T_self, T_m, T_p);
-                a.site_rate[s] = q.pm ? dn_pairs<true, ILP>(P, sm, pair_walk_mask(q.pm), base, dpb0, q.A, q.B, q.sum0) : q.sum0;
+                base_a = __shfl_sync(0xffffffffu, base_a, 0); base_d = __shfl_sync(0xffffffffu, base_d, 0);
+                const uint32_t ent = (uint32_t)(li << 8 | lj << 5 | lane) | (c << 16);
+                if (to_att) {
+                    const int pos = base_a + __popc(b_att & lt_mask);
+                    sm.lw[pos] = w; sm.le[pos] = ent;
+                }
+                if (to_diff) {
+                    const int pos = TL_SITES - 1 - base_d - __popc(b_diff & lt_mask);
+                    sm.lw[pos] = w; sm.le[pos] = ent;
+                }
             }
         }
-        // ---- pass B: occupied sites (diffusion, :79-109) --------------------------------------------------
+        __syncthreads();
+
+        // ---- pass B: the lists, 32 sites per warp and trip; a trip runs one class -----------------------------
+        const int n_att = n_list[0], n_diff = n_list[1];
+        const int nb_att = (n_att + 31) >> 5, nb_all = nb_att + ((n_diff + 31) >> 5);
 #pragma unroll 1
-        for (int b0 = 0; b0 < n_diff; b0 += 32) {
-            if (b0 + lane < n_diff) {
-                const uint64_t w = wl.w[DN_LIST - 1 - b0 - lane];
-                const uint32_t e = wl.e[DN_LIST - 1 - b0 - lane];
-                const int li = (e >> 8) & 3, lj = (e >> 5) & 7, lk = e & 31;
-                const unsigned c = e >> 16;
-                const int rowbase = (li + 2) * TL_HJ + lj + 2;
-                const uint32_t base = po0 + (uint32_t)((rowbase * TL_PK + TL_PK0 + lk) * 8);
-                const int s = ((p0 + li) * L + j0 + lj) * L + k0 + lk;
-                const TilePrep q = tile_prep_occ(P, sm.tab, w, c & 15u, (int)(c >> 4), a.T[s]);
-                a.site_rate[s] = dn_pairs<false, ILP>(P, sm, pair_walk_mask(q.pm), base, dpb0, q.A, q.B, 0.0);
+        for (int b = wid; b < nb_all; b += TL_WARPS) {
+            if (b < nb_att) {                                            // empty sites: nucleation + attachment (kmc_event_rates.py:116-158)
+                const int q = 32 * b + lane;
+                if (q < n_att) {
+                    const uint64_t w = sm.lw[q];
+                    const uint32_t e = sm.le[q];
+                    const int li = (e >> 8) & 3, lj = (e >> 5) & 7, lk = e & 31;
+                    const int rowbase = (li + 2) * TL_HJ + lj + 2;
+                    const uint32_t base = po0 + (uint32_t)((rowbase * TL_PK + TL_PK0 + lk) * 8);
+                    const int k = k0 + lk;
+                    const int s = ((p0 + li) * L + j0 + lj) * L + k;
+                    const double T_self = lds_f64(base);                 // an empty site's pairop is its temperature
+                    double T_m = T_self, T_p = T_self;
+                    if ((uint32_t)w & 0x11111111u || (uint32_t)(w >> 32) & 0x00111111u) {     // an occupied neighbour: grad_z (:151-153)
+                        const uint32_t vaddr = vx0 + (uint32_t)(rowbase * TL_VK + TL_VK0 + lk);
+                        // an empty k neighbour keeps its temperature in pairop
+                        if (k > 0) T_m = (lds_u8<-1>(vaddr) & 15u) == TC_EMPTY ? lds_f64(base - 8u) : a.T[s - 1];
+                        if (k < L - 1) T_p = (lds_u8<1>(vaddr) & 15u) == TC_EMPTY ? lds_f64(base + 8u) : a.T[s + 1];
+                    }
+                    const TilePrep pr = tile_prep_emp(P, sm.tab, w, T_self, T_m, T_p);
+                    a.site_rate[s] = pr.pm ? dn_pairs<true, ILP>(P, sm, pair_walk_mask(pr.pm), base, dpb0, pr.A, pr.B, pr.sum0) : pr.sum0;
+                }
+            } else {                                                     // occupied sites: diffusion (:79-109)
+                const int q = 32 * (b - nb_att) + lane;
+                if (q < n_diff) {
+                    const uint64_t w = sm.lw[TL_SITES - 1 - q];
+                    const uint32_t e = sm.le[TL_SITES - 1 - q];
+                    const int li = (e >> 8) & 3, lj = (e >> 5) & 7, lk = e & 31;
+                    const unsigned c = e >> 16;
+                    const int rowbase = (li + 2) * TL_HJ + lj + 2;
+                    const uint32_t base = po0 + (uint32_t)((rowbase * TL_PK + TL_PK0 + lk) * 8);
+                    const int s = ((p0 + li) * L + j0 + lj) * L + k0 + lk;
+                    const TilePrep pr = tile_prep_occ(P, sm.tab, w, c & 15u, (int)(c >> 4), a.T[s]);
+                    a.site_rate[s] = dn_pairs<false, ILP>(P, sm, pair_walk_mask(pr.pm), base, dpb0, pr.A, pr.B, 0.0);
+                }
             }
         }
         __syncthreads();                                           // the tile and the lists may be overwritten

@@ -550,11 +550,21 @@ __global__ void __launch_bounds__(128) sweep_apply_kernel(const __grid_constant_
         if (cs == key) a.claim[s] = 0ull;
         if (ety == CET_EV_DIFF && ct == key) a.claim[tgt] = 0ull;
     }
+    // one set of atomics per CTA
+    __shared__ int cta_cnt[3];
+    if (threadIdx.x < 3) cta_cnt[threadIdx.x] = 0;
+    __syncthreads();
     fired = warp_sum_i(fired); applied = warp_sum_i(applied); nuc = warp_sum_i(nuc);
     if ((threadIdx.x & 31) == 0) {
-        if (fired) atomicAdd(&a.ss->n_fired_total, (unsigned long long)fired);
-        if (applied) atomicAdd(&a.ss->n_applied, (unsigned long long)applied);
-        if (nuc) atomicAdd(&a.ss->n_nuc, (unsigned long long)nuc);
+        if (fired) atomicAdd(&cta_cnt[0], fired);
+        if (applied) atomicAdd(&cta_cnt[1], applied);
+        if (nuc) atomicAdd(&cta_cnt[2], nuc);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (cta_cnt[0]) atomicAdd(&a.ss->n_fired_total, (unsigned long long)cta_cnt[0]);
+        if (cta_cnt[1]) atomicAdd(&a.ss->n_applied, (unsigned long long)cta_cnt[1]);
+        if (cta_cnt[2]) atomicAdd(&a.ss->n_nuc, (unsigned long long)cta_cnt[2]);
     }
 }
 
