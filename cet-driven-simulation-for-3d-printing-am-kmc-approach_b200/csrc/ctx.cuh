@@ -146,6 +146,7 @@ struct cet_ctx {
     bool tile_valid = false;          // cvox / pairop match vox / theta / phi / T / defects / the state ids
     bool emp_canonical = false;       // no empty site carries an orientation (checked by tile_state_ensure)
     int tile_blocks[6] = {0, 0, 0, 0, 0, 0};
+    int refresh_blocks = 0;           // resident CTAs per SM of rates_refresh_kernel (0 = not yet queried)
     int dense_blocks[2] = {0, 0};     // resident CTAs per SM of rates_dense_kernel<1>, <2> (0 = not yet queried)
     bool compact_attr_set = false; // resident CTAs per SM of the four tile-kernel variants (0 = not yet queried)
     int debug_flags = 0;              // cet_debug_flags: 1 = no TMA (cooperative tile loads), 2 = gather refresh of the first design,

@@ -40,6 +40,8 @@ __global__ void rates_tile_kernel(const __grid_constant__ RateTileArgs a, int s_
 __global__ void dirty_eval_kernel(const __grid_constant__ RateTileArgs a, const int32_t *list, const unsigned int *n_list,
                                   unsigned int *queue);
 
+int rates_refresh_list(cet_ctx *c, const int32_t *list, const unsigned int *counter, int64_t nsite_hint);     // rates_refresh.cu
+
 int rate_tables_ensure(cet_ctx *c)
 {
     if (!c->rate_attr_set) {                 // per device; a context lives on one device
@@ -410,6 +412,8 @@ int rates_rows_dirty_compact(cet_ctx *c, int p_lo, int p_hi, const uint32_t *sta
     dirty_scan_kernel<<<(n_words + RB_WARPS * 32 - 1) / (RB_WARPS * 32), RB_WARPS * 32, 0, c->stream>>>(d);
     CET_CUDA(cudaGetLastError());
     const int64_t nsite = (int64_t)(p_hi - p_lo) * c->plane;
+    // evaluation: the class-sorted kernel of rates_refresh.cu; debug flag 262144 runs the pair-compacting kernel below
+    if (!(c->debug_flags & 262144)) return rates_refresh_list(c, list, counter, nsite);
     const int grid = (int)std::min<int64_t>((nsite + RT_CHUNK * RT_WARPS - 1) / (RT_CHUNK * RT_WARPS), (int64_t)sm_count(c) * 4);   // 4 resident CTAs per SM: measured 0.74 ms per sweep at 512^3 against 0.85 (5), 0.81 (3), 1.46 (6) — the gathers live on the L1 the CTAs leave free
     unsigned int *queue = (unsigned int *)(c->rate_tab + RT_TABLE_DOUBLES) + 1;
     CET_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned int), c->stream));
