@@ -37,7 +37,6 @@ struct RefreshSmem {
     uint64_t lw[RF_CHUNK];                               // class codes of the 14 neighbours, 4 bits per slot
     int32_t ls[RF_CHUNK];                                // local linear site index
     uint32_t lc[RF_CHUNK];                               // own cvox byte | RF_* flags
-    int lin[16];                                         // [15 - o]: linear offset of neighbour slot o
     int n_list[2][2];                                    // [chunk parity][att, diff] list lengths
     unsigned int chunk[2];
 };
@@ -118,14 +117,12 @@ __global__ void __launch_bounds__(RF_THREADS, 4) rates_refresh_kernel(const __gr
     const int n = (int)*a.n_list;
 
     for (int q = tid; q < RT_TABLE_DOUBLES; q += RF_THREADS) sm.tab[q] = a.tab[q];
-    if (tid < 14) sm.lin[15 - tid] = a.lin[tid];
     if (tid == 0) {
         sm.chunk[0] = atomicAdd(a.queue, 1u);
         sm.n_list[0][0] = 0; sm.n_list[0][1] = 0;
     }
     __syncthreads();
     const uint32_t op0 = (uint32_t)__cvta_generic_to_shared(&sm.op[wid][0][lane]);
-    const uint32_t lin0 = (uint32_t)__cvta_generic_to_shared(sm.lin);
 
     for (unsigned it = 0;; ++it) {
         const int64_t c0 = (int64_t)sm.chunk[it & 1u] * RF_CHUNK;
@@ -210,18 +207,19 @@ __global__ void __launch_bounds__(RF_THREADS, 4) rates_refresh_kernel(const __gr
             if (on) { w = sm.lw[pos]; s = sm.ls[pos]; e = sm.lc[pos]; }
             // the site's pair mask and the operand gathers, issued before anything waits
             const uint64_t pm = !on ? 0ull : att ? (w & (w >> 3) & CET_NIB_LSB) : (~w & (w >> 3) & CET_NIB_LSB);
-            uint32_t m = pair_walk_mask(pm);
-            const int cnt = __popc(m);
+            // slot-major, so that the lanes of a warp — consecutive stamped sites, mostly neighbours along k — ask for
+            // neighbouring addresses in the same instruction (a lane-major walk of the masks scatters them)
+            const uint32_t pm_lo = (uint32_t)pm, pm_hi = (uint32_t)(pm >> 32);
+            const int cnt = __popc(pm_lo) + __popc(pm_hi);
             {
                 const double *src = a.pairop + s;
                 uint32_t dst = op0;
-                while (m) {
-                    const int h = 31 - __clz(m);
-                    m &= (1u << h) - 1u;
-                    int off;
-                    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(off) : "r"(lin0 + 2u * (uint32_t)h));
-                    cp_async8(dst, src + off);
-                    dst += 256u;
+#pragma unroll
+                for (int o = 0; o < 14; ++o) {
+                    if ((o < 8 ? pm_lo >> (4 * o) : pm_hi >> (4 * (o - 8))) & 1u) {
+                        cp_async8(dst, src + a.lin[o]);
+                        dst += 256u;
+                    }
                 }
             }
             if (att) {                                                   // empty sites: nucleation + attachment (kmc_event_rates.py:116-158)
