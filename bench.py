@@ -388,24 +388,27 @@ def main():
         return r
 
     refreshed = res["sites_refreshed"] / max(args.steps, 1)
+    # the dense rebuild runs the TMA tile kernel when the rows can be described by a tensor map (sweep_tile.cu:tile_tma_ok)
+    dense_k = "rates_dense_kernel" if (L % 16 == 0 and L >= 64) else "rates_compact_kernel"
+    refresh_name = "dirty_scan + rates_refresh_kernel (neighbour-rate refresh)"
+    dense_name = dense_k + " (dense rebuild after the thermal step)"
     rl = {
         "sweep_stream_kernel": roof("decide", BYTES_STREAM * eval_sites),
-        "dirty_scan + dirty_eval_compact (neighbour-rate refresh)":
+        refresh_name:
             roof("refresh", BYTES_RATES * refreshed + BYTES_STAMP * eval_sites, BYTES_RATES_LAYOUT * refreshed + BYTES_STAMP * eval_sites),
-        "rates_compact_kernel (dense rebuild after the thermal step)":
+        dense_name:
             roof("rates", BYTES_RATES * eval_sites, BYTES_RATES_LAYOUT * eval_sites),
         "thermal_kernel": roof("thermal", BYTES_THERMAL * own_planes * L * L),
     }
     share = {k: prof[k][0] for k in ("decide", "pick", "apply", "refresh", "thermal", "rates", "halo", "allreduce", "boundary")}
     dominant = max(share, key=share.get)
-    dom_name = {"decide": "sweep_stream_kernel", "refresh": "dirty_scan + dirty_eval_compact (neighbour-rate refresh)",
-                "rates": "rates_compact_kernel (dense rebuild after the thermal step)", "thermal": "thermal_kernel"}.get(dominant)
+    dom_name = {"decide": "sweep_stream_kernel", "refresh": refresh_name, "rates": dense_name, "thermal": "thermal_kernel"}.get(dominant)
     traffic = None                   # dram__bytes_read+write per launch of the dominant kernel, from this round's ncu capture
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             per = json.load(f)["per_kernel"]
-        pick_k = {"decide": ["sweep_stream_kernel"], "refresh": ["dirty_scan_kernel", "dirty_eval_compact_kernel"],
-                  "rates": ["rates_compact_kernel"], "thermal": ["thermal_kernel_v2"]}.get(dominant, [])
+        pick_k = {"decide": ["sweep_stream_kernel"], "refresh": ["dirty_scan_kernel", "rates_refresh_kernel"],
+                  "rates": [dense_k], "thermal": ["thermal_kernel_v2"]}.get(dominant, [])
         vals = [v for n in pick_k for k, v in per.items() if n in k]
         traffic = sum(vals) if len(vals) == len(pick_k) and vals else None
     except Exception:

@@ -36,20 +36,24 @@ int sm_count(cet_ctx *c);
 
 constexpr int DN_ROWS = TL_I * TL_J;                     // 32 rows of 32 sites per tile
 constexpr int DN_WROWS = DN_ROWS / TL_WARPS;             // rows per warp in pass A
+constexpr uint32_t DN_LISTED = 1u << 23;
 constexpr int DN_INLINE_MIN = 12;                        // pass A evaluates pairless empty sites itself from this many per row on
 
 struct DenseSmem {
     double po[TL_HI * TL_HJ * TL_PK];                    // 128-byte aligned TMA destinations first
     uint8_t vx[TL_VBYTES];
     double tab[RT_TABLE_DOUBLES];
-    // the tile's two site lists, shared by the CTA (every site is in at most one): empty sites from the front,
-    // occupied sites from the back
+    // the tile's sites as pass A staged them (index = tile-local site index li << 8 | lj << 5 | lk) ...
     uint64_t lw[TL_SITES];                               // class codes of the 14 neighbours, 4 bits per slot
-    uint32_t le[TL_SITES];                               // tile-local site index (li << 8 | lj << 5 | lk) | own cvox byte << 16
+    uint32_t lc[TL_SITES];                               // own cvox byte | sort key << 8 | rank within the key << 13 | DN_LISTED
+    // ... and the order pass B walks them in: by class, then (SORT) by pair count — a trip costs its longest lane,
+    // and unsorted only 17 of 32 lanes were busy in the pair loops
+    uint16_t perm[TL_SITES + 32];
+    int key_cnt[32], key_start[32];                      // sort key: class << 4 | pair count
+    int n_slots;                                         // slots of perm in use (the first class padded to whole trips)
     int16_t dpb[16];                                     // [15 - o]: byte offset of neighbour slot o's pairop from the site's own
     unsigned long long bar;
     int4 tile[2];                                        // {tile index, p0, j0, k0} of this / the next iteration (popped ahead of need)
-    int n_list[2][2];                                    // [tile parity][att, diff] list lengths
 };
 
 struct DenseArgs {
@@ -116,7 +120,7 @@ __device__ __forceinline__ double dn_pairs(const cet_rate_params &P, const Dense
     return sum;
 }
 
-template <int ILP>
+template <bool SORT>
 __global__ void __launch_bounds__(TL_THREADS, 4)
     rates_dense_kernel(const __grid_constant__ DenseArgs a, const __grid_constant__ CUtensorMap tm_vox, const __grid_constant__ CUtensorMap tm_po)
 {
@@ -140,8 +144,8 @@ __global__ void __launch_bounds__(TL_THREADS, 4)
         mbar_init(&sm.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         pop_tile(0);
-        sm.n_list[0][0] = 0; sm.n_list[0][1] = 0;
     }
+    if (tid < 32) sm.key_cnt[tid] = 0;
     __syncthreads();
     const uint32_t vx0 = smem_u32(sm.vx), po0 = smem_u32(sm.po), dpb0 = smem_u32(sm.dpb);
 
@@ -149,13 +153,11 @@ __global__ void __launch_bounds__(TL_THREADS, 4)
         const int4 ti = sm.tile[it & 1u];
         if (ti.x >= a.n_tiles) break;
         const int p0 = ti.y, j0 = ti.z, k0 = ti.w;
-        int *n_list = sm.n_list[it & 1u];
         if (tid == 0) {
             mbar_expect_tx(&sm.bar, (unsigned)(TL_VBYTES + TL_PBYTES));
             tma_load_3d(sm.vx, &tm_vox, &sm.bar, k0 - TL_VK0, j0 - 2, p0 - 2);
             tma_load_3d(sm.po, &tm_po, &sm.bar, k0 - TL_PK0, j0 - 2, p0 - 2);
             pop_tile((it + 1u) & 1u);                                    // read after the barrier that ends this tile
-            sm.n_list[(it + 1u) & 1u][0] = 0; sm.n_list[(it + 1u) & 1u][1] = 0;
         }
         mbar_wait(&sm.bar, it & 1u);
 
@@ -196,42 +198,65 @@ __global__ void __launch_bounds__(TL_THREADS, 4)
                 double dep;
                 a.dep_rate[j * L + k] = (is_emp && dep_rate(P, T_self, &dep)) ? dep : NAN;
             }
-            const unsigned b_att = __ballot_sync(0xffffffffu, to_att), b_diff = __ballot_sync(0xffffffffu, to_diff);
-            if (b_att | b_diff) {
-                int base_a = 0, base_d = 0;
-                if (lane == 0) {
-                    if (b_att) base_a = atomicAdd(&n_list[0], __popc(b_att));
-                    if (b_diff) base_d = atomicAdd(&n_list[1], __popc(b_diff));
-                }
-                base_a = __shfl_sync(0xffffffffu, base_a, 0); base_d = __shfl_sync(0xffffffffu, base_d, 0);
-                const uint32_t ent = (uint32_t)(li << 8 | lj << 5 | lane) | (c << 16);
-                if (to_att) {
-                    const int pos = base_a + __popc(b_att & lt_mask);
-                    sm.lw[pos] = w; sm.le[pos] = ent;
-                }
-                if (to_diff) {
-                    const int pos = TL_SITES - 1 - base_d - __popc(b_diff & lt_mask);
-                    sm.lw[pos] = w; sm.le[pos] = ent;
-                }
+            // stage the site with its sort key and its rank within the key (one shared-memory atomic per distinct key of the warp)
+            const bool listed = to_att || to_diff;
+            const int np = to_att ? __popc(att) : __popc(emp);
+            const int key = (to_att ? 0 : 16) + (SORT ? np : 0);
+            const unsigned peers = __match_any_sync(0xffffffffu, listed ? key : -1);
+            int rank = 0;
+            if (listed) {
+                const int leader = __ffs(peers) - 1;
+                if (lane == leader) rank = atomicAdd(&sm.key_cnt[key], __popc(peers));
+                rank = __shfl_sync(peers, rank, leader) + __popc(peers & lt_mask);
             }
+            const int slot = row * 32 + lane;
+            sm.lw[slot] = w;
+            sm.lc[slot] = listed ? (c | ((uint32_t)key << 8) | ((uint32_t)rank << 13) | DN_LISTED) : 0u;
+        }
+        __syncthreads();
+        // ---- counting sort: start of every key (the occupied class starts on a whole trip) ---------------------------
+        if (wid == 0) {
+            const int cnt = sm.key_cnt[lane];
+            int inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += u;
+            }
+            const int n_emp_cls = __shfl_sync(0xffffffffu, inc, 15), pad = (32 - (n_emp_cls & 31)) & 31;
+            sm.key_start[lane] = inc - cnt + (lane >= 16 ? pad : 0);
+            sm.key_cnt[lane] = 0;                                        // for the next tile
+            if (lane < pad) sm.perm[n_emp_cls + lane] = 0xFFFFu;
+            if (lane == 31) sm.n_slots = inc + pad;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < DN_WROWS; ++r) {
+            const int slot = (wid * DN_WROWS + r) * 32 + lane;
+            const uint32_t e = sm.lc[slot];
+            if (e & DN_LISTED) sm.perm[sm.key_start[(e >> 8) & 31u] + (int)((e >> 13) & 1023u)] = (uint16_t)slot;
         }
         __syncthreads();
 
-        // ---- pass B: the lists, 32 sites per warp and trip; a trip runs one class -----------------------------
-        const int n_att = n_list[0], n_diff = n_list[1];
-        const int nb_att = (n_att + 31) >> 5, nb_all = nb_att + ((n_diff + 31) >> 5);
+        // ---- pass B: 32 sites per warp and trip; a trip runs one class and (SORT) mostly one pair count ------------------
+        const int n_slots = sm.n_slots, nb_all = (n_slots + 31) >> 5;
 #pragma unroll 1
         for (int b = wid; b < nb_all; b += TL_WARPS) {
-            if (b < nb_att) {                                            // empty sites: nucleation + attachment (kmc_event_rates.py:116-158)
-                const int q = 32 * b + lane;
-                if (q < n_att) {
-                    const uint64_t w = sm.lw[q];
-                    const uint32_t e = sm.le[q];
-                    const int li = (e >> 8) & 3, lj = (e >> 5) & 7, lk = e & 31;
-                    const int rowbase = (li + 2) * TL_HJ + lj + 2;
-                    const uint32_t base = po0 + (uint32_t)((rowbase * TL_PK + TL_PK0 + lk) * 8);
-                    const int k = k0 + lk;
-                    const int s = ((p0 + li) * L + j0 + lj) * L + k;
+            const int q = 32 * b + lane;
+            unsigned slot = 0xFFFFu;
+            if (q < n_slots) slot = sm.perm[q];
+            const bool on = slot != 0xFFFFu;
+            uint32_t e = 0;
+            if (on) e = sm.lc[slot];
+            const bool att_trip = __any_sync(0xffffffffu, on && !(e & (16u << 8)));       // a trip holds one class
+            if (on) {
+                const uint64_t w = sm.lw[slot];
+                const int li = (slot >> 8) & 3, lj = (slot >> 5) & 7, lk = slot & 31;
+                const int rowbase = (li + 2) * TL_HJ + lj + 2;
+                const uint32_t base = po0 + (uint32_t)((rowbase * TL_PK + TL_PK0 + lk) * 8);
+                const int k = k0 + lk;
+                const int s = ((p0 + li) * L + j0 + lj) * L + k;
+                if (att_trip) {                                          // empty sites: nucleation + attachment (kmc_event_rates.py:116-158)
                     const double T_self = lds_f64(base);                 // an empty site's pairop is its temperature
                     double T_m = T_self, T_p = T_self;
                     if ((uint32_t)w & 0x11111111u || (uint32_t)(w >> 32) & 0x00111111u) {     // an occupied neighbour: grad_z (:151-153)
@@ -241,20 +266,11 @@ __global__ void __launch_bounds__(TL_THREADS, 4)
                         if (k < L - 1) T_p = (lds_u8<1>(vaddr) & 15u) == TC_EMPTY ? lds_f64(base + 8u) : a.T[s + 1];
                     }
                     const TilePrep pr = tile_prep_emp(P, sm.tab, w, T_self, T_m, T_p);
-                    a.site_rate[s] = pr.pm ? dn_pairs<true, ILP>(P, sm, pair_walk_mask(pr.pm), base, dpb0, pr.A, pr.B, pr.sum0) : pr.sum0;
-                }
-            } else {                                                     // occupied sites: diffusion (:79-109)
-                const int q = 32 * (b - nb_att) + lane;
-                if (q < n_diff) {
-                    const uint64_t w = sm.lw[TL_SITES - 1 - q];
-                    const uint32_t e = sm.le[TL_SITES - 1 - q];
-                    const int li = (e >> 8) & 3, lj = (e >> 5) & 7, lk = e & 31;
-                    const unsigned c = e >> 16;
-                    const int rowbase = (li + 2) * TL_HJ + lj + 2;
-                    const uint32_t base = po0 + (uint32_t)((rowbase * TL_PK + TL_PK0 + lk) * 8);
-                    const int s = ((p0 + li) * L + j0 + lj) * L + k0 + lk;
+                    a.site_rate[s] = pr.pm ? dn_pairs<true, 2>(P, sm, pair_walk_mask(pr.pm), base, dpb0, pr.A, pr.B, pr.sum0) : pr.sum0;
+                } else {                                                 // occupied sites: diffusion (:79-109)
+                    const unsigned c = e & 255u;
                     const TilePrep pr = tile_prep_occ(P, sm.tab, w, c & 15u, (int)(c >> 4), a.T[s]);
-                    a.site_rate[s] = dn_pairs<false, ILP>(P, sm, pair_walk_mask(pr.pm), base, dpb0, pr.A, pr.B, 0.0);
+                    a.site_rate[s] = dn_pairs<false, 2>(P, sm, pair_walk_mask(pr.pm), base, dpb0, pr.A, pr.B, 0.0);
                 }
             }
         }
@@ -262,19 +278,19 @@ __global__ void __launch_bounds__(TL_THREADS, 4)
     }
 }
 
-template <int ILP>
+template <bool SORT>
 static int dense_launch(cet_ctx *c, const DenseArgs &a, int *blocks_per_sm)
 {
     const size_t smem = sizeof(DenseSmem) + 1024;
     if (*blocks_per_sm == 0) {
-        CET_CUDA(cudaFuncSetAttribute(rates_dense_kernel<ILP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CET_CUDA(cudaFuncSetAttribute(rates_dense_kernel<SORT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        CET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rates_dense_kernel<ILP>, TL_THREADS, smem));
+        CET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rates_dense_kernel<SORT>, TL_THREADS, smem));
         CET_REQUIRE(nb >= 1, "rates_dense_kernel does not fit an SM");
         *blocks_per_sm = nb;
     }
     const int grid = std::min(a.n_tiles, sm_count(c) * *blocks_per_sm);
-    rates_dense_kernel<ILP><<<grid, TL_THREADS, smem, c->stream>>>(a, *(const CUtensorMap *)c->tmap_vox, *(const CUtensorMap *)c->tmap_po);
+    rates_dense_kernel<SORT><<<grid, TL_THREADS, smem, c->stream>>>(a, *(const CUtensorMap *)c->tmap_vox, *(const CUtensorMap *)c->tmap_po);
     CET_CUDA(cudaGetLastError());
     return 0;
 }
@@ -296,9 +312,9 @@ int rates_rows_dense(cet_ctx *c, int p_lo, int p_hi)
     a.njb = (int)((c->n1 + TL_J - 1) / TL_J); a.nkb = (int)((c->n2 + TL_K - 1) / TL_K);
     a.n_tiles = ((p_hi - p_lo + TL_I - 1) / TL_I) * a.njb * a.nkb;
     CET_CUDA(cudaMemsetAsync(a.queue, 0, sizeof(unsigned int), c->stream));
-    // pairs in flight per lane and trip: 2 (default) or 1 (debug flag 131072); the same bits either way
-    if (c->debug_flags & 131072) { if (int rc = dense_launch<1>(c, a, &c->dense_blocks[0])) return rc; }
-    else if (int rc = dense_launch<2>(c, a, &c->dense_blocks[1])) return rc;
+    // pass B walks the tile's sites sorted by class and pair count (default) or by class only (debug flag 131072); the same bits
+    if (c->debug_flags & 131072) { if (int rc = dense_launch<false>(c, a, &c->dense_blocks[0])) return rc; }
+    else if (int rc = dense_launch<true>(c, a, &c->dense_blocks[1])) return rc;
     CET_CUDA(cudaGetLastError());
     return 0;
 }

@@ -13,10 +13,10 @@ if [ "$1" = "capture" ]; then
   $T 200 $B > gpurun_out/r02_bench_plain.log 2>&1 && \
     $T 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_bench.csv \
         $B > gpurun_out/r02_ncu_l.log 2>&1
-  $T 300 ncu --set full --clock-control none --import-source on -k regex:"thermal_kernel|rates_compact|tile_pairop" -c 3 \
+  $T 300 ncu --set full --clock-control none --import-source on -k regex:"thermal_kernel|rates_dense|tile_pairop" -c 3 \
     -o gpurun_out/r02_prof_thermal_rates -f $B --steps 2 > gpurun_out/r02_ncu_a.log 2>&1
   $T 400 ncu --set full --clock-control none --import-source on \
-    -k regex:"dirty_eval_compact|dirty_scan|sweep_stream|sweep_pick|sweep_apply|sweep_plane_reduce|sweep_finalize" -s 14 -c 14 \
+    -k regex:"rates_refresh|dirty_scan|sweep_stream|sweep_pick|sweep_apply|sweep_plane_reduce|sweep_finalize" -s 14 -c 14 \
     -o gpurun_out/r02_prof_sweep -f $B --steps 2 > gpurun_out/r02_ncu_b.log 2>&1
   # the measured alternatives of the refresh, same workload: shared-memory tile kernel staged by TMA (flags 48),
   # by vector loads (32), and the gather refresh of the first design (2)

@@ -3,7 +3,7 @@ and level-3 parity (trajectory observables against the serial oracle within stat
 Rate-maintenance variants (Context.debug_flags): COMPACT (default) = stamped sites refreshed by list-driven
 gathers from the compact tile state (class-sorted kernel of rates_refresh.cu; PAIR_COMPACT = the pair-compacting
 kernel of rates.cu), dense rebuilds by the class-sorted TMA tile kernel (rates_dense.cu) when
-L % 16 == 0 (DENSE_ILP1: one pair in flight per lane instead of two); TILE = the refresh's tile kernel for the
+L % 16 == 0 (DENSE_UNSORTED: its pass B walks the sites by class only, not by class and pair count); TILE = the refresh's tile kernel for the
 refresh and the rebuild (TMA staging), VECTOR / SCALAR its other staging modes, SERIAL its per-lane pair
 loop; DENSE_COMPACT = dense rebuilds by the compact gather kernel; GATHER = refresh + rebuild of the first design
 (neighbour-class cache + unit vectors)."""
@@ -20,7 +20,7 @@ def _sweep_params(cet, seed, L, eps=0.02, p_max=0.25, defect_fraction=0.0, therm
     return sp
 
 
-COMPACT, GATHER, TILE, DENSE_COMPACT, DENSE_ILP1, PAIR_COMPACT = 0, 2, 32, 65536, 131072, 262144
+COMPACT, GATHER, TILE, DENSE_COMPACT, DENSE_UNSORTED, PAIR_COMPACT = 0, 2, 32, 65536, 131072, 262144
 SCALAR, SERIAL, VECTOR = TILE | 1, TILE | 4, TILE | 16
 TMA = TILE
 FUSED = COMPACT
@@ -95,7 +95,7 @@ def test_refresh_variants_agree(cet, L):
     and resident rates."""
     from cetkmc._config import thermal_params
     outs = []
-    for flags in (COMPACT, PAIR_COMPACT, DENSE_ILP1, DENSE_COMPACT, TILE, SCALAR, VECTOR, SERIAL, SERIAL | 16, GATHER, COMPACT | 8):
+    for flags in (COMPACT, PAIR_COMPACT, DENSE_UNSORTED, DENSE_COMPACT, TILE, SCALAR, VECTOR, SERIAL, SERIAL | 16, GATHER, COMPACT | 8):
         ctx, st, th, ph, T, df = _setup(cet, L, flags=flags)
         res = ctx.sweep_run(7, _sweep_params(cet, 5, L, eps=0.01, p_max=0.2, defect_fraction=0.01, thermal_every=3),
                             thermal_params(1e-6, nan_to_num=True))
@@ -299,7 +299,7 @@ def test_resident_rates_equal_rebuild_after_sweeps(cet, L, flags):
     np.testing.assert_array_equal(dr1, dr2)
 
 
-@pytest.mark.parametrize("L,flags", [(64, COMPACT), (80, COMPACT), (80, DENSE_ILP1), (96, DENSE_COMPACT)])
+@pytest.mark.parametrize("L,flags", [(64, COMPACT), (80, COMPACT), (80, DENSE_UNSORTED), (96, DENSE_COMPACT)])
 def test_dense_rebuild_edge_cases(cet, oracle, L, flags):
     """The dense rebuild kernels on inputs that leave fast_exp's range and exercise every clamp: cold blocks
     (T below 1 K and a few kelvin: Arrhenius arguments far beyond -700, the out-of-line path), sites at and
