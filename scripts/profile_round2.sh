@@ -18,13 +18,14 @@ if [ "$1" = "capture" ]; then
   $T 400 ncu --set full --clock-control none --import-source on \
     -k regex:"rates_refresh|dirty_scan|sweep_stream|sweep_pick|sweep_apply|sweep_plane_reduce|sweep_finalize" -s 14 -c 14 \
     -o gpurun_out/r02_prof_sweep -f $B --steps 2 > gpurun_out/r02_ncu_b.log 2>&1
-  # the measured alternatives of the refresh, same workload: shared-memory tile kernel staged by TMA (flags 48),
-  # by vector loads (32), and the gather refresh of the first design (2)
-  for f in 48 32 2; do
+  # the measured alternatives, same workload: pair-compacting refresh (262144), dense kernel without the pair-count
+  # sort (131072), dense gather kernel on the compact state (65536), shared-memory tile kernel for refresh + rebuild
+  # staged by TMA (32), gather refresh + rebuild of the first design (2)
+  for f in 262144 131072 65536 32 2; do
     $T 200 $B --debug-flags $f > gpurun_out/r02_bench_flags$f.json 2> gpurun_out/r02_bench_flags$f.err
   done
   $T 300 ncu --set full --clock-control none --import-source on -k regex:"rates_tile3d" -s 2 -c 1 \
-    -o gpurun_out/r02_prof_tile3d_tma -f $B --steps 2 --debug-flags 48 > gpurun_out/r02_ncu_c.log 2>&1
+    -o gpurun_out/r02_prof_tile3d_tma -f $B --steps 2 --debug-flags 32 > gpurun_out/r02_ncu_c.log 2>&1
 else
   $T 400 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err
   $T 300 python bench.py --thermal laser --no-cpu-baseline > gpurun_out/r02_bench_laser.json 2> gpurun_out/r02_bench_laser.err
