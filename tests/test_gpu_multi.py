@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("extra", [["--L", "48", "--sweeps", "10"], ["--L", "40", "--n0", "80", "--sweeps", "16", "--eps", "0.004"],
+                                   ["--L", "64", "--sweeps", "12"],                       # rows a tensor map can describe: the TMA dense kernel on the slabs
                                    ["--L", "64", "--sweeps", "12", "--flags", "32"],      # TMA tile kernel also for the refresh, on the slabs
                                    ["--L", "48", "--sweeps", "10", "--flags", "2"]])      # first-design gather path + full-plane exchange
 def test_slabs_match_single_gpu(cet, extra):
