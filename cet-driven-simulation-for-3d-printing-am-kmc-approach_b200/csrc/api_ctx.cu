@@ -269,6 +269,9 @@ int cet_destroy(cet_ctx *c)
     for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_reduce_ready) cudaEventDestroy(c->ev_reduce_ready);
+    if (c->ev_reduce_done) cudaEventDestroy(c->ev_reduce_done);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;

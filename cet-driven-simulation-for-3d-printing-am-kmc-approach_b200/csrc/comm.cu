@@ -25,6 +25,7 @@ struct NcclApi {
                               cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, void *) = nullptr;      // optional (NCCL >= 2.18)
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -53,6 +54,7 @@ static int nccl_load()
     CET_SYM(GroupEnd, "ncclGroupEnd");
     CET_SYM(GetErrorString, "ncclGetErrorString");
 #undef CET_SYM
+    *(void **)(&g_nccl.CommSplit) = dlsym(h, "ncclCommSplit");
     g_nccl.handle = h;
     return 0;
 }
@@ -154,13 +156,29 @@ int comm_delta_exchange(cet_ctx *c)
 // local maximum, stored contiguously at plane_sum[n].  Every entry is non-zero on at most one
 // rank, so ONE max-all-reduce over n+1 doubles yields both the gathered plane sums (bit-exact,
 // independent of the slab count) and the global maximum.
+// With a second communicator (cet_comm_init splits one off when NCCL offers ncclCommSplit) the reduction runs on
+// the context's side stream: started as soon as the plane sums exist, joined by comm_sweep_reduce_join before the
+// kernel that needs the totals — pick, apply, the delta exchange and the refresh run meanwhile, and the rank skew
+// the reduction would otherwise wait out on the main stream is absorbed.  Without it: in place, on the main stream.
 int comm_sweep_reduce(cet_ctx *c, double *plane_sum, int n, double *max_inout)
 {
     if (c->world <= 1) return 0;
     CET_REQUIRE(c->nccl_comm != nullptr, "sweep reduce: cet_comm_init has not been called");
     CET_REQUIRE(max_inout == plane_sum + n, "sweep reduce: max slot must follow the plane sums");
+    if (c->nccl_comm2) {
+        CET_CUDA(cudaEventRecord(c->ev_reduce_ready, c->stream));
+        CET_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_reduce_ready, 0));
+        CET_NCCL(g_nccl.AllReduce(plane_sum, plane_sum, (size_t)n + 1, ncclDouble, ncclMax, (ncclComm_t)c->nccl_comm2, c->stream2));
+        CET_CUDA(cudaEventRecord(c->ev_reduce_done, c->stream2));
+        return 0;
+    }
     CET_NCCL(g_nccl.AllReduce(plane_sum, plane_sum, (size_t)n + 1, ncclDouble, ncclMax, (ncclComm_t)c->nccl_comm,
                               c->stream));
+    return 0;
+}
+int comm_sweep_reduce_join(cet_ctx *c)
+{
+    if (c->world > 1 && c->nccl_comm2) CET_CUDA(cudaStreamWaitEvent(c->stream, c->ev_reduce_done, 0));
     return 0;
 }
 
@@ -194,6 +212,20 @@ int cet_comm_init(cet_ctx *c, const void *id128, int rank, int world)
     CET_NCCL(g_nccl.CommInitRank(&comm, world, id, rank));
     c->nccl_comm = comm;
     c->rank = rank; c->world = world;
+    // a second communicator + stream for the sweeps' totals reduction (comm_sweep_reduce); optional
+    if (world > 1 && g_nccl.CommSplit && !c->nccl_comm2) {
+        ncclComm_t comm2 = nullptr;
+        if (g_nccl.CommSplit(comm, 0, rank, &comm2, nullptr) == ncclSuccess && comm2) {
+            if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaEventCreateWithFlags(&c->ev_reduce_ready, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&c->ev_reduce_done, cudaEventDisableTiming) == cudaSuccess) {
+                c->nccl_comm2 = comm2;
+            } else {
+                g_nccl.CommDestroy(comm2);
+                (void)cudaGetLastError();
+            }
+        }
+    }
     return 0;
 }
 
@@ -201,6 +233,11 @@ int cet_comm_destroy(cet_ctx *c)
 {
     if (!c || !c->nccl_comm) return 0;
     cet::DeviceGuard dg(c->device);
+    if (c->nccl_comm2) {
+        cudaStreamSynchronize(c->stream2);
+        g_nccl.CommDestroy((ncclComm_t)c->nccl_comm2);
+        c->nccl_comm2 = nullptr;
+    }
     g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
     c->nccl_comm = nullptr;
     c->rank = 0; c->world = 1;

@@ -170,6 +170,9 @@ struct cet_ctx {
 
     // NCCL
     void *nccl_comm = nullptr;
+    void *nccl_comm2 = nullptr;       // split-off communicator for the totals reduction of the sweeps, on stream2 (NULL: none)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_reduce_ready = nullptr, ev_reduce_done = nullptr;
     int rank = 0, world = 1;
     // delta halo exchange of the sweeps (comm.cu): per cut face one send and one receive buffer,
     // [0] lower face, [1] upper face; layout: 16-byte header (entry count) + DeltaEntry[delta_cap]

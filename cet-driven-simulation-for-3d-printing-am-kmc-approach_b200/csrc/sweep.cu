@@ -54,6 +54,7 @@ bool tile_tma_ok(const cet_ctx *c);
 int stamp_fill(cet_ctx *c, int p_lo, int p_hi);
 int rates_rows_dirty_compact(cet_ctx *c, int p_lo, int p_hi, const uint32_t *stamp, int32_t *list, unsigned int *counter);
 int rates_rows_compact(cet_ctx *c, int p_lo, int p_hi);
+int comm_sweep_reduce_join(cet_ctx *c);                                           // comm.cu
 int rates_rows_dense(cet_ctx *c, int p_lo, int p_hi);                            // rates_dense.cu
 int rate_tables_ensure(cet_ctx *c);
 
@@ -760,6 +761,9 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
         c->blk_sum, c->blk_max, tpp, n_eval, i_off + R.eval_lo, (int)c->i_begin, (int)c->i_end,
         c->plane_sum, max_slot);
     CET_CUDA(cudaGetLastError());
+    // the totals are only needed for the next tau (sweep_finalize_kernel, last kernel of the sweep): the reduction
+    // over the slabs starts here — on a side stream when the context has a second communicator — and is joined there
+    if (c->world > 1) if (int rc = comm_sweep_reduce(c, c->plane_sum, (int)c->n0, max_slot)) return rc;
     const int sparse_grid = sm_count(c) * 32;
     ApplyArgs apply_args;
     {
@@ -802,15 +806,6 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
         ProfScope ps(c, PROF_REFRESH);
         if (int rc = refresh_tiled(c, R)) return rc;
     }
-    // the totals are only needed for the next tau: reduce them here, next to the halo exchange, so
-    // that a sweep has one inter-rank synchronisation point instead of two
-    if (c->world > 1) {
-        ProfScope ps(c, PROF_ALLREDUCE);
-        if (int rc = comm_sweep_reduce(c, c->plane_sum, (int)c->n0, max_slot)) return rc;
-    }
-    sweep_finalize_kernel<<<1, 256, 0, c->stream>>>(c->sweep, c->plane_sum, (int)c->n0, max_slot,
-                                                    sp->events_per_sweep, sp->p_max);
-    CET_CUDA(cudaGetLastError());
     if (c->world > 1 && count) {
         if (tiled) {
             // Delta exchange: every slab sends the owned sites it changed within DELTA_ZONE planes of a cut
@@ -857,6 +852,13 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
             }
         }
     }
+    {
+        ProfScope ps(c, PROF_ALLREDUCE);          // what the main stream still waits for the reduction
+        if (int rc = comm_sweep_reduce_join(c)) return rc;
+    }
+    sweep_finalize_kernel<<<1, 256, 0, c->stream>>>(c->sweep, c->plane_sum, (int)c->n0, max_slot,
+                                                    sp->events_per_sweep, sp->p_max);
+    CET_CUDA(cudaGetLastError());
     if (count) c->sweep_index++;
     return 0;
 }
