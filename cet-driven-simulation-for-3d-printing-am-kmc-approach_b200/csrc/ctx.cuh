@@ -145,12 +145,11 @@ struct cet_ctx {
     int *tile_flag = nullptr;
     bool tile_valid = false;          // cvox / pairop match vox / theta / phi / T / defects / the state ids
     bool emp_canonical = false;       // no empty site carries an orientation (checked by tile_state_ensure)
-    int tile_blocks[6] = {0, 0, 0, 0, 0, 0};
+    int tile_blocks[6] = {0, 0, 0, 0, 0, 0};   // resident CTAs per SM of the rates_tile3d_kernel variants (0 = not yet queried)
     int refresh_blocks = 0;           // resident CTAs per SM of rates_refresh_kernel (0 = not yet queried)
-    int dense_blocks[2] = {0, 0};     // resident CTAs per SM of rates_dense_kernel<1>, <2> (0 = not yet queried)
-    bool compact_attr_set = false; // resident CTAs per SM of the four tile-kernel variants (0 = not yet queried)
-    int debug_flags = 0;              // cet_debug_flags: 1 = no TMA (cooperative tile loads), 2 = gather refresh of the first design,
-                                      // 4 = tile kernel walks the 14 slots per lane instead of compacting the pairs across the warp
+    int dense_blocks[2] = {0, 0};     // resident CTAs per SM of rates_dense_kernel<unsorted>, <sorted> (0 = not yet queried)
+    bool compact_attr_set = false;    // shared-memory attribute of the pair-compacting kernels set
+    int debug_flags = 0;              // cet_debug_flags: kernel variants for tests / profiling, bit values in include/cetkmc.h
     alignas(64) unsigned char tmap_vox[128];
     alignas(64) unsigned char tmap_po[128];
     const void *tmap_vox_ptr = nullptr, *tmap_po_ptr = nullptr;

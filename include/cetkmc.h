@@ -216,15 +216,18 @@ int cet_grains_download_planes(cet_ctx *ctx, int64_t i_lo, int64_t i_hi, int32_t
  * (-1 when the cache is declared stale). */
 int cet_debug_nst_mismatches(cet_ctx *ctx, int64_t *n_bad);
 /* Test / profiling hook: which kernels keep the rate sums current in cet_sweep_run (all variants give
- * the same bits).  Default: stamped sites are refreshed by list-driven gathers from the compact tile state
- * (class codes + pair operands); the dense rebuild after a thermal step runs the shared-memory tile kernel
- * staged by 3-D TMA boxes when L % 16 == 0, the dense gather kernel on the compact state otherwise.
+ * the same bits).  Default: stamped sites are refreshed by the class-sorted list kernel on the compact tile
+ * state (class codes + pair operands; rates_refresh.cu); the dense rebuild after a thermal step runs the
+ * class-sorted tile kernel staged by 3-D TMA boxes (rates_dense.cu) when L % 16 == 0 and L >= 64, the dense
+ * gather kernel on the compact state otherwise.
+ * 262144: refresh by the pair-compacting list kernel (rates.cu); 131072: the dense tile kernel walks its sites by
+ * class only, without the sort by pair count; 65536: dense rebuilds by the compact gather kernel;
  * 2: the gather refresh + dense kernel of the first design (neighbour-class cache + unit vectors);
- * 32: the tile kernel also for the refresh; 1: tile kernel staged by scalar loads, 16: by 16-byte vector loads;
- * 4: the tile kernel walks the 14 neighbour slots per lane instead of compacting the pairs across the warp;
- * 8: dense rebuilds by the first design's gather kernel; 65536: dense rebuilds by the compact gather kernel;
+ * 32: the shared-memory tile kernel of sweep_tile.cu for the refresh and the rebuild; 1: that kernel staged by
+ * scalar loads, 16: by 16-byte vector loads; 4: it walks the 14 neighbour slots per lane instead of compacting
+ * the pairs across the warp; 8: dense rebuilds by the first design's gather kernel;
  * 64 / 128: timing probes of the apply kernel (stamps / field writes skipped: results invalid);
- * bits 8-15: stamped sites per warp and queue entry of the refresh, in units of 32 (0 = default 64). */
+ * bits 8-15: stamped sites per warp and queue entry of the pair-compacting refresh, in units of 32 (0 = default 64). */
 int cet_debug_flags(cet_ctx *ctx, int flags);
 
 /* ---- per-kernel device timing: CUDA event pairs recorded on the context stream around every
