@@ -31,6 +31,16 @@ __device__ __forceinline__ double warp_max(double v)
     return v;
 }
 
+// max of non-negative, non-NaN doubles: their order is the order of their bit patterns, so two integer warp
+// reductions (REDUX) replace the five shuffle + fmax steps
+__device__ __forceinline__ double warp_max_nonneg(double v)
+{
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
+
 // Row sums split by occupancy class; lane l adds k = l, l+32, ... in order, then xor tree.
 __device__ __forceinline__ void warp_row_sums(const uint8_t *vox_row, const double *rate_row, int n2,
                                               double *occ, double *emp)

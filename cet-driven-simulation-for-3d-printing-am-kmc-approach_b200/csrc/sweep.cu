@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(ST_THREADS, 6) sweep_stream_kernel(const __gri
         }
     }
     rsum = warp_sum(rsum);
-    rmax = warp_max(rmax);
+    rmax = warp_max_nonneg(rmax);                 // rate sums are >= +0 and never NaN (keep_rate)
     if (lane == 0) { s_sum[w] = rsum; s_max[w] = rmax; }
     // fired sites: staged per CTA (one global list reservation per CTA: a reservation per warp would put
     // ~4e5 atomics per sweep on one address); a CTA with more than ST_STAGE of them appends the rest directly
@@ -852,7 +852,7 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
             }
         }
     }
-    {
+    if (c->world > 1) {
         ProfScope ps(c, PROF_ALLREDUCE);          // what the main stream still waits for the reduction
         if (int rc = comm_sweep_reduce_join(c)) return rc;
     }
