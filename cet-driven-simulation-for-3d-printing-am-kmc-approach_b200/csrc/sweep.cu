@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(ST_THREADS, 6) sweep_stream_kernel(const __gri
     __shared__ unsigned int s_cnt, s_base;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
-    const int pl = blockIdx.x / a.tiles_per_plane, tile = blockIdx.x % a.tiles_per_plane;
+    const int pl = blockIdx.y, tile = blockIdx.x;                   // grid: (tiles per plane, evaluated planes)
+    const int blk = pl * a.tiles_per_plane + tile;
     const int p = a.p_lo + pl;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const double tau = a.ss->terminated ? 0.0 : a.ss->tau;
@@ -160,15 +161,30 @@ __global__ void __launch_bounds__(ST_THREADS, 6) sweep_stream_kernel(const __gri
                                       (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
         const uint32_t words[4] = {r.x, r.y, r.z, r.w};
         const double tau16 = tau * 65536.0;
+        // pre-filter: else digit > floor(65536 x) >= floor(65536 p): cannot fire
+        unsigned cand = 0;
 #pragma unroll
         for (int e = 0; e < ST_PER_THREAD; ++e) {
             const uint32_t digit = (words[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
             const double d = __hiloint2double(0x43300000, (int)digit) - 4503599627370496.0;   // (double)digit
-            if (d <= R[e] * tau16) {                            // else digit > floor(65536 x) >= floor(65536 p): cannot fire
-                const int site = qw + (e >> 1) * 64 + (e & 1);
-                if (stream_fire_exact(R[e] * tau, d, a.seed, (uint64_t)(a.i_off + p) * (uint64_t)a.plane_sites + (uint64_t)site, a.sweep))
-                    fmask |= 1u << e;
-            }
+            if (d <= R[e] * tau16) cand |= 1u << e;
+        }
+        // the survivors (~0.5 % of the sites) take the exact test; one loop for all eight positions, so the lanes
+        // of a warp that hold a survivor run it together and the streaming part above holds no call
+        while (cand) {
+            const int e = __ffs(cand) - 1;
+            cand &= cand - 1;
+            double Re = R[0];
+            uint32_t wd = words[0];
+#pragma unroll
+            for (int q = 1; q < ST_PER_THREAD; ++q) if (e == q) Re = R[q];
+#pragma unroll
+            for (int q = 1; q < 4; ++q) if ((e >> 1) == q) wd = words[q];
+            const uint32_t digit = (wd >> (16 * (e & 1))) & 0xFFFFu;
+            const double d = __hiloint2double(0x43300000, (int)digit) - 4503599627370496.0;
+            const int site = qw + (e >> 1) * 64 + (e & 1);
+            if (stream_fire_exact(Re * tau, d, a.seed, (uint64_t)(a.i_off + p) * (uint64_t)a.plane_sites + (uint64_t)site, a.sweep))
+                fmask |= 1u << e;
         }
     }
     rsum = warp_sum(rsum);
@@ -205,8 +221,8 @@ __global__ void __launch_bounds__(ST_THREADS, 6) sweep_stream_kernel(const __gri
     if (threadIdx.x == 0) {
         double t = 0.0, m = 0.0;
         for (int q = 0; q < ST_THREADS / 32; ++q) { t += s_sum[q]; m = fmax(m, s_max[q]); }
-        a.blk_sum[blockIdx.x] = t;
-        a.blk_max[blockIdx.x] = m;
+        a.blk_sum[blk] = t;
+        a.blk_max[blk] = m;
         const unsigned int n = min(s_cnt, (unsigned)ST_STAGE);
         s_base = n ? atomicAdd(&a.ss->n_fired, n) : 0u;
     }
@@ -754,7 +770,7 @@ static int sweep_once(cet_ctx *c, const cet_sweep_params *sp, const cet_thermal_
         a.plane_sites = (int)c->plane; a.tiles_per_plane = tpp; a.i_off = i_off;
         a.seed = sp->seed; a.sweep = (uint32_t)c->sweep_index;
         ProfScope ps(c, PROF_DECIDE);
-        sweep_stream_kernel<<<n_eval * tpp, ST_THREADS, 0, c->stream>>>(a);
+        sweep_stream_kernel<<<dim3((unsigned)tpp, (unsigned)n_eval), ST_THREADS, 0, c->stream>>>(a);
     }
     CET_CUDA(cudaGetLastError());
     sweep_plane_reduce_kernel<<<(n_eval + 3) / 4, 128, 0, c->stream>>>(
