@@ -146,7 +146,7 @@ struct cet_ctx {
     bool tile_valid = false;          // cvox / pairop match vox / theta / phi / T / defects / the state ids
     bool emp_canonical = false;       // no empty site carries an orientation (checked by tile_state_ensure)
     int tile_blocks[6] = {0, 0, 0, 0, 0, 0};   // resident CTAs per SM of the rates_tile3d_kernel variants (0 = not yet queried)
-    int refresh_blocks = 0;           // resident CTAs per SM of rates_refresh_kernel (0 = not yet queried)
+    int refresh_blocks[3] = {0, 0, 0};   // resident CTAs per SM of rates_refresh_kernel<1 / 2 / 4> (0 = not yet queried)
     int dense_blocks[2] = {0, 0};     // resident CTAs per SM of rates_dense_kernel<unsorted>, <sorted> (0 = not yet queried)
     bool compact_attr_set = false;    // shared-memory attribute of the pair-compacting kernels set
     int debug_flags = 0;              // cet_debug_flags: kernel variants for tests / profiling, bit values in include/cetkmc.h

@@ -26,12 +26,13 @@ int rate_tables_ensure(cet_ctx *c);      // rates.cu
 int sm_count(cet_ctx *c);
 
 constexpr int RF_THREADS = 256, RF_WARPS = RF_THREADS / 32;
-constexpr int RF_ROWS = 2;                               // 32-site rows per warp and chunk in pass A
-constexpr int RF_CHUNK = RF_WARPS * RF_ROWS * 32;        // stamped sites per CTA and queue entry (small: the resident CTAs stay
-                                                         // within a few planes of each other and share their sectors in L2)
+// ROWS = 32-site rows per warp and chunk in pass A; a chunk (RF_WARPS * ROWS * 32 stamped sites) is what a CTA pops from
+// the queue: small, so that the resident CTAs stay within a few planes of each other and share their sectors in L2
 enum { RF_KM_EMPTY = 1u << 8, RF_KP_EMPTY = 1u << 9, RF_K_GT0 = 1u << 10, RF_K_LTL = 1u << 11 };
 
+template <int ROWS>
 struct RefreshSmem {
+    static constexpr int RF_CHUNK = RF_WARPS * ROWS * 32;
     double op[RF_WARPS][14][32];                         // pair operands of the trip a warp is evaluating: [rank][lane]
     double tab[RT_TABLE_DOUBLES];
     uint64_t lw[RF_CHUNK];                               // class codes of the 14 neighbours, 4 bits per slot
@@ -106,10 +107,12 @@ __device__ __forceinline__ double rf_pairs(const cet_rate_params &P, const doubl
     return sum;
 }
 
+template <int ROWS>
 __global__ void __launch_bounds__(RF_THREADS, 4) rates_refresh_kernel(const __grid_constant__ RefreshArgs a)
 {
+    constexpr int RF_CHUNK = RF_WARPS * ROWS * 32, RF_ROWS = ROWS;
     extern __shared__ __align__(16) unsigned char refresh_dyn_smem[];
-    RefreshSmem &sm = *reinterpret_cast<RefreshSmem *>(refresh_dyn_smem);
+    RefreshSmem<ROWS> &sm = *reinterpret_cast<RefreshSmem<ROWS> *>(refresh_dyn_smem);
     const cet_rate_params &P = a.P;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int L = a.L, LL = L * L;
@@ -256,6 +259,24 @@ __global__ void __launch_bounds__(RF_THREADS, 4) rates_refresh_kernel(const __gr
     }
 }
 
+template <int ROWS>
+static int refresh_launch(cet_ctx *c, const RefreshArgs &a, int64_t nsite_hint, int *blocks_per_sm)
+{
+    constexpr int CHUNK = RF_WARPS * ROWS * 32;
+    const size_t smem = sizeof(RefreshSmem<ROWS>);
+    if (*blocks_per_sm == 0) {
+        CET_CUDA(cudaFuncSetAttribute(rates_refresh_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rates_refresh_kernel<ROWS>, RF_THREADS, smem));
+        CET_REQUIRE(nb >= 1, "rates_refresh_kernel does not fit an SM");
+        *blocks_per_sm = nb;
+    }
+    const int grid = (int)std::min<int64_t>((nsite_hint + CHUNK - 1) / CHUNK, (int64_t)sm_count(c) * *blocks_per_sm);
+    rates_refresh_kernel<ROWS><<<grid, RF_THREADS, smem, c->stream>>>(a);
+    CET_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // Re-evaluate the sites listed in `list` (length *counter, produced by dirty_scan_kernel) from cvox / pairop.
 int rates_refresh_list(cet_ctx *c, const int32_t *list, const unsigned int *counter, int64_t nsite_hint)
 {
@@ -273,18 +294,12 @@ int rates_refresh_list(cet_ctx *c, const int32_t *list, const unsigned int *coun
     a.mLL = (unsigned int)((1ull << 32) / (uint64_t)c->plane) + 1u;
     a.mL = (unsigned int)((1ull << 32) / (uint64_t)c->n1) + 1u;
     for (int o = 0; o < 14; ++o) a.lin[o] = (h_nb_off[o][0] * a.L + h_nb_off[o][1]) * a.L + h_nb_off[o][2];
-    if (c->refresh_blocks == 0) {
-        CET_CUDA(cudaFuncSetAttribute(rates_refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RefreshSmem)));
-        int nb = 0;
-        CET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rates_refresh_kernel, RF_THREADS, sizeof(RefreshSmem)));
-        CET_REQUIRE(nb >= 1, "rates_refresh_kernel does not fit an SM");
-        c->refresh_blocks = nb;
-    }
     CET_CUDA(cudaMemsetAsync(a.queue, 0, sizeof(unsigned int), c->stream));
-    const int grid = (int)std::min<int64_t>((nsite_hint + RF_CHUNK - 1) / RF_CHUNK, (int64_t)sm_count(c) * c->refresh_blocks);
-    rates_refresh_kernel<<<grid, RF_THREADS, sizeof(RefreshSmem), c->stream>>>(a);
-    CET_CUDA(cudaGetLastError());
-    return 0;
+    // stamped sites per CTA and queue entry: 512 (default), 256 / 1024 by debug flag 1048576 / 2097152
+    const int v = (c->debug_flags & 1048576) ? 0 : (c->debug_flags & 2097152) ? 2 : 1;
+    if (v == 0) return refresh_launch<1>(c, a, nsite_hint, &c->refresh_blocks[0]);
+    if (v == 2) return refresh_launch<4>(c, a, nsite_hint, &c->refresh_blocks[2]);
+    return refresh_launch<2>(c, a, nsite_hint, &c->refresh_blocks[1]);
 }
 
 }  // namespace cet

@@ -95,7 +95,7 @@ def test_refresh_variants_agree(cet, L):
     and resident rates."""
     from cetkmc._config import thermal_params
     outs = []
-    for flags in (COMPACT, PAIR_COMPACT, DENSE_UNSORTED, DENSE_COMPACT, TILE, SCALAR, VECTOR, SERIAL, SERIAL | 16, GATHER, COMPACT | 8):
+    for flags in (COMPACT, COMPACT | 1048576, COMPACT | 2097152, PAIR_COMPACT, DENSE_UNSORTED, DENSE_COMPACT, TILE, SCALAR, VECTOR, SERIAL, SERIAL | 16, GATHER, COMPACT | 8):
         ctx, st, th, ph, T, df = _setup(cet, L, flags=flags)
         res = ctx.sweep_run(7, _sweep_params(cet, 5, L, eps=0.01, p_max=0.2, defect_fraction=0.01, thermal_every=3),
                             thermal_params(1e-6, nan_to_num=True))
