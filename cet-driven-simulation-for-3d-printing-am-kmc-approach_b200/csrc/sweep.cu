@@ -83,7 +83,7 @@ __device__ __forceinline__ unsigned long long claim_key(int rank, long long gsit
 // remaining digits from a second Philox block.  P(fire) = floor(65536 p)/65536 + P(u' < frac)/65536 = p.
 // Fired sites are staged in 2 KB of shared memory and appended with one list reservation per CTA;
 // 6 CTAs per SM stay resident (96 KB of loads in flight per SM).
-constexpr int ST_THREADS = 256, ST_PER_THREAD = 8, ST_TILE = ST_THREADS * ST_PER_THREAD, ST_STAGE = 512;
+constexpr int ST_THREADS = 256, ST_PER_THREAD = 8, ST_TILE = ST_THREADS * ST_PER_THREAD, ST_STAGE = 512, ST_CAND = 512;
 
 struct StreamArgs {
     const double *site_rate, *dep_rate;   // dep_rate: plane of the global top (NaN = no event)
@@ -112,12 +112,24 @@ __device__ __noinline__ bool stream_fire_exact(double x, double d, uint64_t seed
     return u_rest < p16 - f;
 }
 
+// a fired site: staged per CTA, or appended to the global list directly once the staging area is full
+__device__ __forceinline__ void stream_append(const StreamArgs &a, int *s_list, unsigned int *s_cnt, int32_t site)
+{
+    const unsigned int q = atomicAdd(s_cnt, 1u);
+    if (q < ST_STAGE) { s_list[q] = site; return; }
+    const unsigned int g = atomicAdd(&a.ss->n_fired, 1u);
+    if (g < a.cap_fired) a.fired[g] = site;
+    else a.ss->overflow = 1;
+}
+
 __global__ void __launch_bounds__(ST_THREADS, 6) sweep_stream_kernel(const __grid_constant__ StreamArgs a)
 {
     __shared__ double s_sum[ST_THREADS / 32], s_max[ST_THREADS / 32];
     __shared__ int s_list[ST_STAGE];
-    __shared__ unsigned int s_cnt, s_base;
-    if (threadIdx.x == 0) s_cnt = 0;
+    __shared__ double c_R[ST_CAND];                 // staged survivors of the digit pre-filter: rate sum ...
+    __shared__ uint32_t c_sd[ST_CAND];              // ... site within the tile << 16 | leading digit
+    __shared__ unsigned int s_cnt, s_base, s_ncand;
+    if (threadIdx.x == 0) { s_cnt = 0; s_ncand = 0; }
     __syncthreads();
     const int pl = blockIdx.y, tile = blockIdx.x;                   // grid: (tiles per plane, evaluated planes)
     const int blk = pl * a.tiles_per_plane + tile;
@@ -154,7 +166,6 @@ __global__ void __launch_bounds__(ST_THREADS, 6) sweep_stream_kernel(const __gri
     double rsum = 0.0, rmax = 0.0;
 #pragma unroll
     for (int e = 0; e < ST_PER_THREAD; ++e) { rsum += R[e]; rmax = fmax(rmax, R[e]); }
-    unsigned fmask = 0;
     if (tau > 0.0 && rmax > 0.0) {
         const uint32_t tid_in_plane = (uint32_t)(tile * ST_THREADS + threadIdx.x);
         const u32x4 r = philox4x32_10(u32x4{tid_in_plane, (uint32_t)(a.i_off + p), a.sweep, (uint32_t)STREAM_FIRE},
@@ -169,8 +180,8 @@ __global__ void __launch_bounds__(ST_THREADS, 6) sweep_stream_kernel(const __gri
             const double d = __hiloint2double(0x43300000, (int)digit) - 4503599627370496.0;   // (double)digit
             if (d <= R[e] * tau16) cand |= 1u << e;
         }
-        // the survivors (~0.5 % of the sites) take the exact test; one loop for all eight positions, so the lanes
-        // of a warp that hold a survivor run it together and the streaming part above holds no call
+        // the survivors (~0.5 % of the sites, about one per warp) are staged for the CTA: evaluated where they
+        // arise, each exact test (an expm1, ~140 instructions) would run with one lane of its warp
         while (cand) {
             const int e = __ffs(cand) - 1;
             cand &= cand - 1;
@@ -181,53 +192,43 @@ __global__ void __launch_bounds__(ST_THREADS, 6) sweep_stream_kernel(const __gri
 #pragma unroll
             for (int q = 1; q < 4; ++q) if ((e >> 1) == q) wd = words[q];
             const uint32_t digit = (wd >> (16 * (e & 1))) & 0xFFFFu;
-            const double d = __hiloint2double(0x43300000, (int)digit) - 4503599627370496.0;
-            const int site = qw + (e >> 1) * 64 + (e & 1);
-            if (stream_fire_exact(Re * tau, d, a.seed, (uint64_t)(a.i_off + p) * (uint64_t)a.plane_sites + (uint64_t)site, a.sweep))
-                fmask |= 1u << e;
+            const uint32_t st = (uint32_t)(qw - tile * ST_TILE + (e >> 1) * 64 + (e & 1));      // site within the tile
+            const unsigned int pos = atomicAdd(&s_ncand, 1u);
+            if (pos < ST_CAND) {
+                c_R[pos] = Re; c_sd[pos] = st << 16 | digit;
+            } else {                                            // staging full (only at high firing probabilities): test it here
+                const double d = __hiloint2double(0x43300000, (int)digit) - 4503599627370496.0;
+                const uint64_t gsite = (uint64_t)(a.i_off + p) * (uint64_t)a.plane_sites + (uint64_t)(tile * ST_TILE) + st;
+                if (stream_fire_exact(Re * tau, d, a.seed, gsite, a.sweep)) stream_append(a, s_list, &s_cnt, (int32_t)(base + tile * ST_TILE + (int)st));
+            }
         }
     }
     rsum = warp_sum(rsum);
     rmax = warp_max_nonneg(rmax);                 // rate sums are >= +0 and never NaN (keep_rate)
     if (lane == 0) { s_sum[w] = rsum; s_max[w] = rmax; }
-    // fired sites: staged per CTA (one global list reservation per CTA: a reservation per warp would put
-    // ~4e5 atomics per sweep on one address); a CTA with more than ST_STAGE of them appends the rest directly
-    if (__ballot_sync(0xffffffffu, fmask != 0)) {
-        const int mine = __popc(fmask);
-        int inc = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += u;
-        }
-        unsigned int q0 = 0;
-        if (lane == 31) q0 = atomicAdd(&s_cnt, (unsigned)inc);
-        q0 = __shfl_sync(0xffffffffu, q0, 31) + (unsigned)(inc - mine);
-        while (fmask) {
-            const int e = __ffs(fmask) - 1;
-            fmask &= fmask - 1;
-            const int32_t site = (int32_t)(base + qw + (e >> 1) * 64 + (e & 1));
-            if (q0 < ST_STAGE) {
-                s_list[q0] = site;
-            } else {
-                const unsigned int g = atomicAdd(&a.ss->n_fired, 1u);
-                if (g < a.cap_fired) a.fired[g] = site;
-                else a.ss->overflow = 1;
-            }
-            ++q0;
-        }
-    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    // exact tests of the staged survivors, one per thread; fired sites are staged per CTA (one global list
+    // reservation per CTA: a reservation per warp would put ~4e5 atomics per sweep on one address); a CTA with
+    // more than ST_STAGE of them appends the rest directly
+    const unsigned int ncand = min(s_ncand, (unsigned)ST_CAND);
+    for (unsigned int q = threadIdx.x; q < ncand; q += ST_THREADS) {
+        const double Re = c_R[q];
+        const uint32_t sd = c_sd[q], st = sd >> 16;
+        const double d = __hiloint2double(0x43300000, (int)(sd & 0xFFFFu)) - 4503599627370496.0;   // (double)digit
+        const uint64_t gsite = (uint64_t)(a.i_off + p) * (uint64_t)a.plane_sites + (uint64_t)(tile * ST_TILE) + st;
+        if (stream_fire_exact(Re * tau, d, a.seed, gsite, a.sweep)) stream_append(a, s_list, &s_cnt, (int32_t)(base + tile * ST_TILE + (int)st));
+    }
+    if (threadIdx.x == ST_THREADS - 1) {          // the tile's totals, meanwhile
         double t = 0.0, m = 0.0;
         for (int q = 0; q < ST_THREADS / 32; ++q) { t += s_sum[q]; m = fmax(m, s_max[q]); }
         a.blk_sum[blk] = t;
         a.blk_max[blk] = m;
-        const unsigned int n = min(s_cnt, (unsigned)ST_STAGE);
-        s_base = n ? atomicAdd(&a.ss->n_fired, n) : 0u;
     }
+    if (ncand == 0 && s_ncand == 0) return;       // nothing could fire in this tile (uniform: s_ncand is final after the barrier)
+    __syncthreads();
     const unsigned int n_staged = min(s_cnt, (unsigned)ST_STAGE);
     if (n_staged == 0) return;
+    if (threadIdx.x == 0) s_base = atomicAdd(&a.ss->n_fired, n_staged);
     __syncthreads();
     for (unsigned int q = threadIdx.x; q < n_staged; q += ST_THREADS) {
         if (s_base + q < a.cap_fired) a.fired[s_base + q] = s_list[q];
