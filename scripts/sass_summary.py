@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "cet-driven-simulation-for-3d-printing-am-kmc-approach_b200", "libcetkmc.so")
 GROUPS = [
     ("LDG.128", r"^LDG\.E(\.\w+)*\.128"), ("LDG.64", r"^LDG\.E(\.\w+)*\.64"), ("LDG.U8/S8", r"^LDG\.E(\.\w+)*\.[US]8"),
-    ("LDG other", r"^LDG"), ("STG", r"^STG"), ("RED/ATOMG", r"^(RED|ATOMG|ATOM)\b"), ("ATOMS", r"^ATOMS"),
+    ("LDGSTS (cp.async)", r"^LDGSTS"), ("LDG other", r"^LDG"), ("STG", r"^STG"), ("RED/ATOMG", r"^(RED|ATOMG|ATOM)\b"), ("ATOMS", r"^ATOMS"),
     ("LDS", r"^LDS"), ("STS", r"^STS"), ("UTMALDG (TMA)", r"^UTMALDG"), ("SYNCS (mbarrier)", r"^SYNCS"),
     ("BAR", r"^BAR"), ("SHFL", r"^SHFL"), ("REDUX", r"^REDUX"), ("DFMA", r"^DFMA"), ("DMUL", r"^DMUL"), ("DADD", r"^DADD"),
     ("DSETP", r"^DSETP"), ("MUFU", r"^MUFU"), ("IMAD*", r"^IMAD"), ("LOP3", r"^LOP3"), ("POPC", r"^POPC"),
@@ -36,8 +36,9 @@ def main(out):
     with open(out, "w") as f:
         f.write(f"# SASS summary of libcetkmc.so ({', '.join(arch)}; `cuobjdump -sass`, scripts/sass_summary.py)\n\n"
                 "Static instruction counts per kernel (not execution counts).  The TMA path shows as `UTMALDG` + `SYNCS`\n"
-                "(mbarrier) in `rates_tile3d_kernel<0, *>`; the streaming kernels load with `LDG.E.128`; the refresh /\n"
-                "pick kernels gather class codes with `LDG.E.U8` and pair operands with `LDG.E.64`.\n\n")
+                "(mbarrier) in `rates_dense_kernel` (the default dense rate kernel) and `rates_tile3d_kernel<0, *>`; the\n"
+                "streaming kernels load with `LDG.E.128`; the refresh kernel gathers class codes with `LDG.E.U8` and fetches\n"
+                "its pair operands with `LDGSTS` (cp.async, 8 bytes each); the pick kernel gathers with `LDG.E.U8` / `LDG.E.64`.\n\n")
         f.write("| kernel | SASS instr | " + " | ".join(g for g, _ in GROUPS) + " |\n|---|---|" + "---|" * len(GROUPS) + "\n")
         for k, ins in kernels.items():
             if not ins:
@@ -53,8 +54,8 @@ def main(out):
                         used[q] = True
                 counts.append(n)
             f.write(f"| `{k[:70]}` | {len(ins)} | " + " | ".join(str(c) if c else "" for c in counts) + " |\n")
-        f.write("\n## Excerpt: the TMA issue of `rates_tile3d_kernel<0, 0>` (two 3-D boxes on one mbarrier)\n\n```\n")
-        tma = [k for k in kernels if k.startswith("void cet::rates_tile3d_kernel<0, 0>")]
+        f.write("\n## Excerpt: the TMA issue of `rates_dense_kernel<true>` (two 3-D boxes on one mbarrier)\n\n```\n")
+        tma = [k for k in kernels if k.startswith("void cet::rates_dense_kernel<true>")]
         if tma:
             ins = kernels[tma[0]]
             for q, i in enumerate(ins):
