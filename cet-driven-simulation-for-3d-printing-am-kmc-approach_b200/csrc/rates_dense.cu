@@ -2,24 +2,25 @@
 // parameter change) from the compact tile state: the rate kernel of kmc_event_rates.py:43-160 for the sweep path.
 //
 // The pass is bound by instruction issue and the FP64 pipe, not by HBM: an attachment pair
-// costs one fp64 exp (17 FP64 instructions = 34 pipe cycles per warp), a diffusion pair one reciprocal, and a
+// costs one fp64 exp (15 FP64 instructions = 30 pipe cycles per warp), a diffusion pair one reciprocal, and a
 // site next to a solid/empty interface owns up to 14 of them.  What the counters of the earlier kernels said
 // (997 warp instructions per 32 sites, only 110 of them FP64) is that everything AROUND the arithmetic has to
-// go, so this kernel is built to execute little else:
-//   * a CTA stages a 4 x 8 x 32 tile of cvox + pairop with its halo of 2 by two 3-D TMA boxes (zero fill
-//     outside the lattice = class code 0 = "outside": no bounds logic anywhere); neighbour classes and pair
-//     operands are LDS with immediate offsets from one base register per site;
-//   * warps are autonomous inside a tile (4 rows each).  Pass A reads the 15 class codes of a site, packs them
-//     4 bits per slot, and only CLASSIFIES: sites without events store 0, empty sites without an occupied
-//     neighbour evaluate their nucleation rate on the spot when they are the bulk of the row (the melt above the
-//     front), everything else is appended to the warp's list of its class — empty sites from the front,
-//     occupied sites from the back;
-//   * pass B evaluates the two lists 32 sites at a time, so a trip runs ONE class: the per-site half
-//     (tile_prep_emp / tile_prep_occ: one exp each) without the other class's lanes idling beside it, then
-//     every lane walks its own pair mask in slot order with the running sum in a register — no descriptors, no
-//     shared-memory round trip for operands or rates, and the association order of site_rate_sum for free.
-// The arithmetic is the shared inline code of site_rates.cuh / tile_state.cuh, so the result equals the
-// per-event code, the refresh kernels and the other dense kernels bit for bit (tests/test_gpu_sweep.py).
+// go, so this kernel is built to execute little else (477 per 32 sites):
+//   * persistent CTAs pop 4 x 8 x 32 tiles from a queue; one thread stages cvox + pairop with their halo of 2 by
+//     two 3-D TMA boxes (zero fill outside the lattice = class code 0 = "outside": no bounds logic anywhere);
+//     neighbour classes and pair operands are LDS with immediate offsets from one base register per site;
+//   * pass A (4 rows per warp) reads the 15 class codes of a site, packs them 4 bits per slot, and only
+//     CLASSIFIES: sites without events store 0, empty sites without an occupied neighbour evaluate their
+//     nucleation rate on the spot when they are the bulk of the row (the melt above the front), everything else
+//     is staged with the key (class, number of pairs) and counting-sorted over the tile;
+//   * pass B deals trips of 32 sorted sites to the warps, so a trip runs ONE class — the per-site half
+//     (tile_prep_emp / tile_prep_occ: one exp each) without the other class's lanes idling beside it — and
+//     almost always ONE pair count; then every lane walks its own pair mask in slot order with the running sum
+//     in a register: no descriptors, no shared-memory round trip for operands or rates, and the association
+//     order of site_rate_sum for free.  (The sort costs nothing in locality here: the whole neighbourhood is in
+//     shared memory.  The list-driven refresh, rates_refresh.cu, gathers from global memory and must not sort.)
+// The arithmetic is the shared inline code of site_rates.cuh / tile_state.cuh / pair_walk.cuh, so the result
+// equals the per-event code, the refresh kernels and the other dense kernels bit for bit (tests/test_gpu_sweep.py).
 #include <cuda.h>
 #include <algorithm>
 #include <utility>
