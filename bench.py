@@ -467,6 +467,20 @@ def main():
                       "what": f"run_kmc_sublattice_slab: upload packed state+theta+phi+T from pinned host memory, {args.steps} "
                               "sweeps, download packed state+theta+phi into pinned host memory; one call.  The sweep has no "
                               "reference-signature counterpart; the reference-signature calls are timed under api_e2e"}
+        # the same call over one metrics interval of the reference (METRIC_UPDATE_STEP = 200, kmc_simulation.py:335: the
+        # cadence at which its loop hands the lattice to the host code): the copies are paid once per 200 sweeps
+        n_long = 200
+        barrier()
+        t0 = time.perf_counter()
+        r = run_kmc_sublattice_slab(ctx, hp, hth, hph, hT, n_long, sp, tp, out=res_out)
+        barrier()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        out["e2e"]["per_metrics_interval"] = {"value": sites_total * n_long / dt, "unit": "site-updates/s", "sweeps_per_call": n_long,
+                                              "h2d_bytes_per_step": h2d / n_long, "d2h_bytes_per_step": d2h / n_long}
         del res_keep
     ctx.close()
     del packed, th, ph, T
